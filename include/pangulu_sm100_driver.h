@@ -1,0 +1,80 @@
+/* pangulu_sm100_driver.h -- the host driver that ships with the sm_100a platform module.
+ *
+ * It exports PanguLU's public API for the numeric-factorisation path with the reference's own
+ * prototypes (reference include/pangulu.h:11-15, include/pangulu_interface_common.h:3-20), so a program
+ * written against PanguLU (e.g. its examples/example.c) runs against this library unchanged:
+ *
+ *     pangulu_init  -> reorder (METIS_NodeND when available) + symbolic + block storage + static schedule
+ *     pangulu_gstrf -> numeric LU on the GPU through the platform C ABI (pangulu_platform_0201001.h)
+ *     pangulu_gstrs -> block forward/backward substitution on the host copies of L and U
+ *
+ * Out of scope here (kept as the reference's own code when the module is used inside PanguLU): MC64,
+ * MPI distribution, the dynamic scheduler.  See DESIGN.md.
+ */
+#ifndef PANGULU_SM100_DRIVER_H
+#define PANGULU_SM100_DRIVER_H
+
+#include "pangulu_platform_0201001.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/pangulu_common.h:67-70 */
+typedef pangulu_exblock_ptr sparse_pointer_t;
+typedef pangulu_exblock_idx sparse_index_t;
+typedef calculate_type sparse_value_t;
+
+/* reference include/pangulu_interface_common.h:3-20 */
+typedef struct pangulu_init_options
+{
+    int nthread;
+    int nb;
+    int gpu_kernel_warp_per_block;
+    int gpu_data_move_warp_per_block;
+    int sizeof_value;
+    int is_complex_matrix;
+    float mpi_recv_buffer_level;
+} pangulu_init_options;
+typedef struct pangulu_gstrf_options { char unused_; } pangulu_gstrf_options;
+typedef struct pangulu_gstrs_options { char unused_; } pangulu_gstrs_options;
+
+/* reference include/pangulu.h:11-15 */
+void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse_pointer_t *csc_colptr, sparse_index_t *csc_rowidx,
+                  sparse_value_t *csc_value, pangulu_init_options *init_options, void **pangulu_handle);
+void pangulu_gstrf(pangulu_gstrf_options *gstrf_options, void **pangulu_handle);
+void pangulu_gstrs(sparse_value_t *rhs, pangulu_gstrs_options *gstrs_options, void **pangulu_handle);
+void pangulu_gssv(sparse_value_t *rhs, pangulu_gstrf_options *gstrf_options, pangulu_gstrs_options *gstrs_options, void **pangulu_handle);
+void pangulu_finalize(void **pangulu_handle);
+
+/* Driver options, set BEFORE pangulu_init (the reference takes rank/size from MPI_COMM_WORLD):
+ *   "rank", "nproc"   position in the p x q rank grid (one rank per GPU)
+ *   "ordering"        0 natural (input already permuted), 1 METIS_NodeND, -1 (default) METIS when built in
+ *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan
+ *   "verbose"         1 prints the reference's info lines
+ *   "host_only"       1 builds ordering/symbolic/blocks/schedule in host memory only (CPU-side tests of the
+ *                     host logic); pangulu_gstrf on such a handle is a fatal error -- there is no CPU path
+ * returns 0, -1 for an unknown key. */
+int pangulu_sm100_driver_config(const char *key, long long value);
+
+/* numbers about an initialised handle: "n","nb","block_length","symbolic_nnz","nnz_blocks","num_slots",
+ * "num_own_offdiag","num_own_diag","nwave","ntask","n_getrf","n_tstrf","n_gessm","n_ssssm","flop",
+ * "flop_<class>","bytes_<class>","value_bytes","own_value_bytes","buffer_bytes","p","q","time_<phase>" */
+double pangulu_sm100_driver_info(void *handle, const char *key);
+/* i-th block slot this rank holds (order of the reference's bins[0], then mirrored remote blocks) */
+pangulu_storage_slot_t *pangulu_sm100_driver_slot(void *handle, long long i);
+/* 0 row_perm, 1 col_perm, 2 metis_perm (u32[n]); 3 row_scale, 4 col_scale (T[n]) */
+const void *pangulu_sm100_driver_perm(void *handle, int which);
+/* the static schedule: tasks sorted by wave, wave_ptr has nwave+1 entries */
+const pangulu_task_t *pangulu_sm100_driver_tasks(void *handle, const pangulu_uint64_t **wave_ptr);
+/* put the values of A back into the host block buffers (and the device copy) so gstrf can run again */
+void pangulu_sm100_driver_reset_values(void *handle, int also_device);
+/* device -> host copy of the owned factors (resident mode) */
+void pangulu_sm100_driver_download(void *handle);
+/* the reference's gstrf self-check ||L(U1) - A1|| / ||A1|| (src/pangulu_numeric.c:1082-1341) on host factors */
+double pangulu_sm100_driver_factor_check(void *handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

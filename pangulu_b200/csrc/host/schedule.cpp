@@ -1,0 +1,261 @@
+// schedule.cpp -- static task schedule of the block LU and the flop/byte models.
+//
+// The reference discovers ready tasks at run time with per-block dependency counters, a min-heap and a
+// per-destination SSSSM aggregator (src/pangulu_numeric.c, src/pangulu_task.c, counters from
+// src/pangulu_preprocessing.c:130-315).  The dependency structure itself is static -- it only depends on
+// the block pattern -- so this driver resolves it once, on the host, into WAVES:
+//
+//   depth(k,k) = 1 + max over updates S(k,k,l) of max(depth(k,l), depth(l,k))          (0 without updates)
+//   depth(i,k) = 1 + max(depth(k,k), max over updates S(i,k,l) of max(depth(i,l), depth(l,k)))
+//
+// Wave w holds, in this order: every SSSSM update whose destination has depth w (all updates of a
+// destination are applied together, right before the destination is finalised -- the aggregator's lazy
+// flush, src/pangulu_task.c:39-91, made static), then GETRF of the diagonal blocks of depth w, then
+// TSTRF/GESSM of the off-diagonal blocks of depth w.  Tasks inside a wave are independent except
+// same-destination SSSSMs, which the platform combines per destination.
+// Owner computes (src/pangulu_numeric.c:51,70,93,148): a rank lists only tasks whose destination it owns.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "host_internal.h"
+
+namespace pdrv {
+
+namespace {
+struct Proto
+{
+    int32_t wave;
+    int8_t cls;  // 0 SSSSM, 1 GETRF, 2 TSTRF/GESSM
+    int16_t kernel;
+    eidx row, col, level;
+    int64_t dst, op1, op2;  // slot indices
+};
+}  // namespace
+
+void build_schedule(BlockStore& B, Schedule& S)
+{
+    const eidx bl = B.block_length;
+    const size_t nblk = B.bcol_ptr[bl];
+    S.depth_offdiag.assign(nblk, 0);
+    S.depth_diag.assign(bl, 0);
+    std::vector<int32_t> maxdep_off(nblk, -1), maxdep_diag(bl, -1);
+    std::vector<Proto> protos;
+    std::vector<eidx> R;
+    std::vector<int64_t> gid_l, gid_u;
+
+    auto slot_off = [&](int64_t gid) { return B.slot_of_block[gid]; };
+
+    for (eidx k = 0; k < bl; ++k)
+    {
+        // R = block rows below the diagonal in block column k (= block columns right of it in block row k)
+        R.clear();
+        gid_l.clear();
+        gid_u.clear();
+        for (eptr g = B.bcol_ptr[k]; g < B.bcol_ptr[k + 1]; ++g)
+            if (B.bcol_row[g] > k) { R.push_back(B.bcol_row[g]); gid_l.push_back((int64_t)g); }
+        for (eidx j : R) gid_u.push_back(B.find_block(k, j));
+
+        const int32_t dk = maxdep_diag[k] + 1;
+        S.depth_diag[k] = dk;
+        if (B.owner(k, k) == B.rank)
+        {
+            Proto t{dk, 1, PANGULU_TASK_GETRF, k, k, k, B.slot_of_diag[k], -1, -1};
+            protos.push_back(t);
+            S.n_getrf++;
+        }
+        for (size_t a = 0; a < R.size(); ++a)
+        {
+            const int32_t dl = 1 + std::max(dk, maxdep_off[gid_l[a]]);
+            const int32_t du = 1 + std::max(dk, maxdep_off[gid_u[a]]);
+            S.depth_offdiag[gid_l[a]] = dl;
+            S.depth_offdiag[gid_u[a]] = du;
+            if (B.owner(R[a], k) == B.rank)
+            {
+                // op1 = the diagonal block (lower-half slot; the platform picks the half it needs)
+                Proto t{dl, 2, PANGULU_TASK_TSTRF, R[a], k, k, slot_off(gid_l[a]), B.slot_of_diag[k], -1};
+                protos.push_back(t);
+                S.n_tstrf++;
+            }
+            if (B.owner(k, R[a]) == B.rank)
+            {
+                Proto t{du, 2, PANGULU_TASK_GESSM, k, R[a], k, slot_off(gid_u[a]), B.slot_of_diag[k], -1};
+                protos.push_back(t);
+                S.n_gessm++;
+            }
+        }
+        // updates S(i,j,k), i,j in R, destination block (i,j) must exist
+        for (size_t b = 0; b < R.size(); ++b)
+        {
+            const eidx j = R[b];
+            const int32_t du = S.depth_offdiag[gid_u[b]];
+            // walk block column j against R
+            eptr g = B.bcol_ptr[j];
+            const eptr ge = B.bcol_ptr[j + 1];
+            for (size_t a = 0; a < R.size(); ++a)
+            {
+                const eidx i = R[a];
+                const int32_t m = std::max(S.depth_offdiag[gid_l[a]], du);
+                if (i == j)
+                {
+                    maxdep_diag[i] = std::max(maxdep_diag[i], m);
+                    if (B.owner(i, i) == B.rank)
+                    {
+                        Proto t{0, 0, PANGULU_TASK_SSSSM, i, i, k, B.slot_of_diag[i], slot_off(gid_l[a]), slot_off(gid_u[b])};
+                        protos.push_back(t);
+                        S.n_ssssm++;
+                    }
+                    continue;
+                }
+                while (g < ge && B.bcol_row[g] < i) ++g;
+                if (g < ge && B.bcol_row[g] == i)
+                {
+                    maxdep_off[g] = std::max(maxdep_off[g], m);
+                    if (B.owner(i, j) == B.rank)
+                    {
+                        Proto t{0, 0, PANGULU_TASK_SSSSM, i, j, k, slot_off((int64_t)g), slot_off(gid_l[a]), slot_off(gid_u[b])};
+                        protos.push_back(t);
+                        S.n_ssssm++;
+                    }
+                }
+            }
+        }
+    }
+    // wave of an update = depth of its destination (known only after all levels were seen)
+    int32_t nwave = 0;
+    for (auto& t : protos)
+    {
+        if (t.cls == 0)
+        {
+            if (t.row == t.col) t.wave = S.depth_diag[t.row];
+            else t.wave = S.depth_offdiag[B.find_block(t.row, t.col)];
+        }
+        nwave = std::max(nwave, t.wave + 1);
+    }
+    // bucket by (wave, class), stable
+    std::vector<uint64_t> cnt((size_t)nwave * 3 + 1, 0);
+    for (auto& t : protos) cnt[(size_t)t.wave * 3 + t.cls + 1]++;
+    for (size_t i = 1; i < cnt.size(); ++i) cnt[i] += cnt[i - 1];
+    S.wave_ptr.resize((size_t)nwave + 1);
+    for (int32_t w = 0; w <= nwave; ++w) S.wave_ptr[w] = cnt[(size_t)w * 3];
+    S.tasks.resize(protos.size());
+    std::vector<uint64_t> cur(cnt.begin(), cnt.end() - 1);
+    for (auto& t : protos)
+    {
+        pangulu_task_t& o = S.tasks[cur[(size_t)t.wave * 3 + t.cls]++];
+        memset(&o, 0, sizeof o);
+        o.row = t.row;
+        o.col = t.col;
+        o.kernel_id = t.kernel;
+        o.task_level = t.level;
+        o.compare_flag = t.level;
+        o.opdst = &B.slots[t.dst];
+        o.op1 = t.op1 >= 0 ? &B.slots[t.op1] : nullptr;
+        o.op2 = t.op2 >= 0 ? &B.slots[t.op2] : nullptr;
+        if ((t.op1 < 0 && t.kernel != PANGULU_TASK_GETRF) || (t.op2 < 0 && t.kernel == PANGULU_TASK_SSSSM) || t.dst < 0)
+        {
+            fprintf(stderr, "[PanguLU ERROR] schedule: task (%u,%u,l=%u,k=%d) references a block this rank does not hold\n", t.row, t.col, t.level, (int)t.kernel);
+            exit(EXIT_FAILURE);
+        }
+    }
+}
+
+// Reference flop model (src/pangulu_kernel_interface.c:4-176) in closed form.  The merge loops of the
+// reference count matching index pairs; on patterns closed under symbolic fill (which build_blocks
+// produces) every candidate matches, which gives per task
+//   GETRF  sum over levels l with m_l = |L(:,l)|:  m_l + 2 m_l^2
+//   TSTRF  sum over entries (r,c) of B:            1 + 2 (|U(c,:)| - 1)
+//   GESSM  sum over entries (r,c) of B:            2 |L(:,r)|
+//   SSSSM  sum over entries (t,j) of B:            2 |A(:,t)|
+// (tests/test_flop_model.py checks the closed forms against the merge-based oracle and the reference's own
+// -DPANGULU_PERF counter).  Bytes per task are the algorithmic figures of SURVEY.md 8(d).
+void work_model(const BlockStore& B, const Schedule& S, WorkModel& W)
+{
+    const int nb = B.nb;
+    const double sv = sizeof(T), si = sizeof(iidx), P = sizeof(iptr) * (double)(nb + 1);
+    // row counts of upper blocks used as op2 (entries per row t of B), computed once per block
+    std::vector<std::vector<uint16_t>> rowcnt(B.slots.size());
+    auto get_rowcnt = [&](const pangulu_storage_slot_t* s) -> const std::vector<uint16_t>& {
+        const size_t id = (size_t)(s - B.slots.data());
+        std::vector<uint16_t>& v = rowcnt[id];
+        if (v.empty())
+        {
+            v.assign((size_t)nb, 0);
+            const iptr nnz = s->columnpointer[nb];
+            for (iptr e = 0; e < nnz; ++e) v[s->rowindex[e]]++;
+        }
+        return v;
+    };
+    // fill the cache serially (cheap, O(nnz) once per op2 block), then sum tasks in parallel
+    for (const pangulu_task_t& t : S.tasks)
+        if (t.kernel_id == PANGULU_TASK_SSSSM) get_rowcnt(t.op2);
+        else if (t.kernel_id == PANGULU_TASK_GESSM) get_rowcnt(t.opdst);
+
+    double fg = 0, ft = 0, fe = 0, fs = 0, bg = 0, bt = 0, be = 0, bs = 0;
+#pragma omp parallel for schedule(dynamic, 4096) reduction(+ : fg, ft, fe, fs, bg, bt, be, bs)
+    for (int64_t ti = 0; ti < (int64_t)S.tasks.size(); ++ti)
+    {
+        const pangulu_task_t& t = S.tasks[ti];
+        auto colcnt = [&](const pangulu_storage_slot_t* s, int c) { return (double)(s->columnpointer[c + 1] - s->columnpointer[c]); };
+        auto nnz = [&](const pangulu_storage_slot_t* s) { return (double)s->columnpointer[nb]; };
+        switch (t.kernel_id)
+        {
+        case PANGULU_TASK_GETRF:
+        {
+            const pangulu_storage_slot_t* lo = t.opdst->is_upper ? t.opdst->related_block : t.opdst;
+            const pangulu_storage_slot_t* up = lo->related_block;
+            double f = 0;
+            for (int l = 0; l < nb; ++l)
+            {
+                if (up->columnpointer[l] == up->columnpointer[l + 1]) continue;
+                const double m = colcnt(lo, l);
+                f += m + 2.0 * m * m;
+            }
+            fg += f;
+            bg += (nnz(lo) + nnz(up)) * (2 * sv + si) + 2 * P;
+            break;
+        }
+        case PANGULU_TASK_TSTRF:
+        {
+            const pangulu_storage_slot_t* lo = t.op1->is_upper ? t.op1->related_block : t.op1;
+            const pangulu_storage_slot_t* up = lo->related_block;
+            double f = 0;
+            for (int c = 0; c < nb; ++c)
+            {
+                const double bc = colcnt(t.opdst, c);
+                if (bc > 0) f += bc * (1.0 + 2.0 * (colcnt(up, c) - 1.0));
+            }
+            ft += f;
+            bt += nnz(up) * (sv + si) + nnz(t.opdst) * (2 * sv + si) + 2 * P;
+            break;
+        }
+        case PANGULU_TASK_GESSM:
+        {
+            const pangulu_storage_slot_t* lo = t.op1->is_upper ? t.op1->related_block : t.op1;
+            const std::vector<uint16_t>& rc = rowcnt[(size_t)(t.opdst - B.slots.data())];
+            double f = 0;
+            for (int r = 0; r < nb; ++r)
+                if (rc[r]) f += 2.0 * rc[r] * colcnt(lo, r);
+            fe += f;
+            be += nnz(lo) * (sv + si) + nnz(t.opdst) * (2 * sv + si) + 2 * P;
+            break;
+        }
+        case PANGULU_TASK_SSSSM:
+        {
+            const std::vector<uint16_t>& rc = rowcnt[(size_t)(t.op2 - B.slots.data())];
+            double f = 0;
+            for (int k = 0; k < nb; ++k)
+                if (rc[k]) f += 2.0 * rc[k] * colcnt(t.op1, k);
+            fs += f;
+            double nc = nnz(t.opdst);
+            if (t.opdst->brow_pos == t.opdst->bcol_pos) nc += nnz(t.opdst->related_block);
+            bs += nnz(t.op1) * (sv + si) + nnz(t.op2) * (sv + si) + nc * (2 * sv + si) + 3 * P;
+            break;
+        }
+        }
+    }
+    W.flop_getrf = fg; W.flop_tstrf = ft; W.flop_gessm = fe; W.flop_ssssm = fs;
+    W.bytes_getrf = bg; W.bytes_tstrf = bt; W.bytes_gessm = be; W.bytes_ssssm = bs;
+}
+
+}  // namespace pdrv

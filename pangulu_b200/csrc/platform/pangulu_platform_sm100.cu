@@ -1,0 +1,726 @@
+// pangulu_platform_sm100.cu -- C ABI of the sm_100a platform module (include/pangulu_platform_0201001.h).
+//
+// Host side of the module: translates PanguLU's host task arrays (pangulu_task_t with pointers to host
+// slot structs) into device-resident descriptor arrays, groups same-destination SSSSM tasks, and
+// launches ONE grid per kernel class per batch on the module's stream.  There is no CPU fallback:
+// every failure prints "[PanguLU ERROR] ..." and exits, as the reference platform does
+// (src/platforms/02_NONSHAREDMEM/01_GPU/000_CUDA/pangulu_platform_0201000.cu:31-50).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pangulu_platform_0201001.h"
+#include "sm100_kernels.cuh"
+
+// globals of the PanguLU core (src/pangulu.c:7-9); absent when the module is used stand-alone
+extern "C" {
+extern int pangulu_gpu_kernel_warp_per_block __attribute__((weak));
+extern int pangulu_gpu_data_move_warp_per_block __attribute__((weak));
+extern int pangulu_gpu_shared_mem_size __attribute__((weak));
+}
+
+namespace {
+
+using namespace psm;
+typedef calculate_type T;
+
+#define PSM_STR2(x) #x
+#define PSM_STR(x) PSM_STR2(x)
+
+[[noreturn]] void fatal(const char* file, int line, const char* what, const char* detail)
+{
+    fprintf(stderr, "[PanguLU ERROR] sm100 platform: %s%s%s at %s:%d\n", what, detail ? ": " : "", detail ? detail : "", file, line);
+    fflush(stderr);
+    exit(EXIT_FAILURE);
+}
+#define CK(call)                                                                       \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) fatal(__FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+#define CK_LAST() CK(cudaGetLastError())
+
+enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_NCLASS = 6 };
+
+struct Options
+{
+    long long eager_download = 1;
+    long long dense_threshold = 250;
+    long long ssssm_mode = 0;
+    long long profile = 0;
+};
+
+// pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
+struct Slab
+{
+    char* h = nullptr;
+    char* d = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+};
+
+struct Ctx
+{
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    Options opt;
+    std::vector<Slab> slabs;
+    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0};
+    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0};
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int max_smem_optin = 0;
+    int sm_count = 0;
+};
+Ctx g;
+
+void ensure_ctx()
+{
+    if (g.stream) return;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (g.stream) return;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        fatal(__FILE__, __LINE__, "no CUDA device visible; this module has no CPU path", e != cudaSuccess ? cudaGetErrorString(e) : nullptr);
+    CK(cudaGetDevice(&g.device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, g.device));
+    if (prop.major < 10)
+        fatal(__FILE__, __LINE__, "device is not sm_100-class; the module is built for sm_100a only", prop.name);
+    g.max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g.sm_count = prop.multiProcessorCount;
+    // blocking stream: the PanguLU receiver thread issues H2D copies on the legacy NULL stream
+    // (src/pangulu_communication.c:1850,1880); a blocking stream orders against them like the
+    // reference's NULL-stream kernels do.
+    cudaStream_t s;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamDefault));
+    CK(cudaEventCreate(&g.ev0));
+    CK(cudaEventCreate(&g.ev1));
+    g.stream = s;
+}
+
+Slab& take_slab(size_t bytes)
+{
+    for (auto& s : g.slabs)
+    {
+        if (s.busy && cudaEventQuery(s.done) == cudaSuccess) s.busy = false;
+    }
+    for (auto& s : g.slabs)
+        if (!s.busy && s.cap >= bytes) { s.busy = true; return s; }
+    // none free & large enough: if the pool is big, wait for the oldest busy one that fits
+    if (g.slabs.size() >= 16)
+    {
+        for (auto& s : g.slabs)
+            if (s.cap >= bytes) { CK(cudaEventSynchronize(s.done)); s.busy = true; return s; }
+    }
+    Slab s;
+    s.cap = std::max<size_t>(bytes, (size_t)1 << 20);
+    CK(cudaHostAlloc((void**)&s.h, s.cap, cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&s.d, s.cap));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    s.busy = true;
+    g.slabs.push_back(s);
+    return g.slabs.back();
+}
+
+// ---- slot -> device descriptor ------------------------------------------------------------------
+inline u32 slot_nnz(int nb, const pangulu_storage_slot_t* s) { return s->columnpointer[nb]; }
+
+// CSC view (off-diagonal blocks and the LOWER half of a diagonal block)
+inline Blk<T> blk_csc(const pangulu_storage_slot_t* s)
+{
+    Blk<T> b;
+    b.val = (T*)s->d_value;
+    b.ptr = s->d_columnpointer;
+    b.idx = s->d_rowindex;
+    const bool mirror = s->brow_pos > s->bcol_pos;
+    b.rptr = mirror ? s->d_rowpointer : nullptr;
+    b.ridx = mirror ? s->d_columnindex : nullptr;
+    b.rmap = mirror ? s->d_idx_of_csc_value_for_csr : nullptr;
+    return b;
+}
+// UPPER half of a diagonal block: CSR held in d_rowpointer/d_columnindex (src/pangulu_storage.c:346-352)
+inline Blk<T> blk_upper_diag(const pangulu_storage_slot_t* s)
+{
+    Blk<T> b;
+    b.val = (T*)s->d_value;
+    b.ptr = s->d_rowpointer;
+    b.idx = s->d_columnindex;
+    b.rptr = nullptr; b.ridx = nullptr; b.rmap = nullptr;
+    return b;
+}
+inline BlkRO<T> blk_ro(const pangulu_storage_slot_t* s)
+{
+    BlkRO<T> b;
+    b.val = (const T*)s->d_value;
+    b.ptr = s->d_columnpointer;
+    b.idx = s->d_rowindex;
+    return b;
+}
+inline void diag_halves(pangulu_storage_slot_t* s, pangulu_storage_slot_t*& lower, pangulu_storage_slot_t*& upper)
+{
+    if (s->is_upper) { upper = s; lower = s->related_block; }
+    else { lower = s; upper = s->related_block; }
+    if (!lower || !upper) fatal(__FILE__, __LINE__, "diagonal block without its related half", nullptr);
+}
+
+// ---- batch program: what one hybrid_batched call / one plan wave turns into --------------------------
+struct Step
+{
+    int kind;          // KClass of the launch, or -1 for a device->host value download
+    size_t off;        // first descriptor (index into the class's array)
+    size_t count;      // descriptors (GETRF tasks / panel tasks / SSSSM destinations)
+};
+struct Download { void* h; const void* d; size_t bytes; };
+
+struct Program
+{
+    std::vector<GetrfTask<T>> getrf;
+    std::vector<PanelTask<T>> panel;
+    std::vector<SsssmDest<T>> dests;
+    std::vector<SsssmPair<T>> pairs;
+    std::vector<Step> steps;
+    std::vector<Download> downloads;  // referenced by steps of kind -1 (off/count)
+};
+
+struct DevProgram
+{
+    GetrfTask<T>* getrf = nullptr;
+    PanelTask<T>* panel = nullptr;
+    SsssmDest<T>* dests = nullptr;
+    SsssmPair<T>* pairs = nullptr;
+};
+
+// Append the tasks [t0,t1) -- executed in array order like the reference's serial loop
+// (pangulu_platform_0201000.cu:880-897) -- as maximal runs of one kernel class.
+void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, size_t t1, bool eager_download)
+{
+    size_t i = t0;
+    std::vector<size_t> order;
+    while (i < t1)
+    {
+        const int kid = tasks[i].kernel_id;
+        if (kid == PANGULU_TASK_SSSSM)
+        {
+            size_t j = i;
+            while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_SSSSM) ++j;
+            // group by destination (a diagonal destination is identified by its LOWER half), keeping
+            // the array order of the updates of one destination
+            order.resize(j - i);
+            for (size_t k = 0; k < j - i; ++k) order[k] = i + k;
+            auto key = [&](size_t k) -> const void* {
+                pangulu_storage_slot_t* d = tasks[k].opdst;
+                if (d->brow_pos == d->bcol_pos && d->is_upper) return d->related_block;
+                return d;
+            };
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
+            Step st; st.kind = K_SSSSM_SPARSE; st.off = P.dests.size(); st.count = 0;
+            const void* cur = nullptr;
+            for (size_t k : order)
+            {
+                const pangulu_task_t& t = tasks[k];
+                if (key(k) != cur)
+                {
+                    cur = key(k);
+                    SsssmDest<T> D;
+                    memset(&D, 0, sizeof D);
+                    pangulu_storage_slot_t* d = t.opdst;
+                    if (d->brow_pos == d->bcol_pos)
+                    {
+                        pangulu_storage_slot_t *lo, *up;
+                        diag_halves(d, lo, up);
+                        D.c = blk_csc(lo);
+                        D.c.rptr = nullptr; D.c.ridx = nullptr; D.c.rmap = nullptr;
+                        D.u = blk_upper_diag(up);
+                        D.nnz_c = slot_nnz(nb, lo) + slot_nnz(nb, up);
+                    }
+                    else
+                    {
+                        D.c = blk_csc(d);
+                        D.nnz_c = slot_nnz(nb, d);
+                    }
+                    D.pair_begin = (u32)P.pairs.size();
+                    D.pair_end = D.pair_begin;
+                    P.dests.push_back(D);
+                    st.count++;
+                }
+                SsssmPair<T> pr;
+                pr.a = blk_ro(t.op1);
+                pr.b = blk_ro(t.op2);
+                P.pairs.push_back(pr);
+                P.dests.back().pair_end = (u32)P.pairs.size();
+            }
+            P.steps.push_back(st);
+            i = j;
+        }
+        else if (kid == PANGULU_TASK_GETRF)
+        {
+            size_t j = i;
+            Step st; st.kind = K_GETRF; st.off = P.getrf.size(); st.count = 0;
+            Step dl; dl.kind = -1; dl.off = P.downloads.size(); dl.count = 0;
+            while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_GETRF)
+            {
+                pangulu_storage_slot_t *lo, *up;
+                diag_halves(tasks[j].opdst, lo, up);
+                GetrfTask<T> G;
+                G.lower = blk_csc(lo);
+                G.upper = blk_upper_diag(up);
+                P.getrf.push_back(G);
+                st.count++;
+                if (eager_download)
+                {
+                    P.downloads.push_back({lo->value, lo->d_value, sizeof(T) * (size_t)slot_nnz(nb, lo)});
+                    P.downloads.push_back({up->value, up->d_value, sizeof(T) * (size_t)slot_nnz(nb, up)});
+                    dl.count += 2;
+                }
+                ++j;
+            }
+            P.steps.push_back(st);
+            if (dl.count) P.steps.push_back(dl);
+            i = j;
+        }
+        else if (kid == PANGULU_TASK_TSTRF || kid == PANGULU_TASK_GESSM)
+        {
+            size_t j = i;
+            Step st; st.kind = K_TSTRF; st.off = P.panel.size(); st.count = 0;
+            Step dl; dl.kind = -1; dl.off = P.downloads.size(); dl.count = 0;
+            while (j < t1 && (tasks[j].kernel_id == PANGULU_TASK_TSTRF || tasks[j].kernel_id == PANGULU_TASK_GESSM))
+            {
+                const pangulu_task_t& t = tasks[j];
+                pangulu_storage_slot_t *lo, *up;
+                diag_halves(t.op1, lo, up);
+                PanelTask<T> Q;
+                memset(&Q, 0, sizeof Q);
+                Q.kind = t.kernel_id;
+                Q.b = blk_csc(t.opdst);
+                if (t.kernel_id == PANGULU_TASK_TSTRF)
+                {
+                    if (!Q.b.rptr) fatal(__FILE__, __LINE__, "TSTRF destination has no CSR mirror (must be a strictly-lower block)", nullptr);
+                    Q.diag = blk_upper_diag(up);
+                }
+                else
+                {
+                    Q.diag = blk_csc(lo);
+                }
+                P.panel.push_back(Q);
+                st.count++;
+                if (eager_download)
+                {
+                    P.downloads.push_back({t.opdst->value, t.opdst->d_value, sizeof(T) * (size_t)slot_nnz(nb, t.opdst)});
+                    dl.count++;
+                }
+                ++j;
+            }
+            P.steps.push_back(st);
+            if (dl.count) P.steps.push_back(dl);
+            i = j;
+        }
+        else
+        {
+            char msg[64];
+            snprintf(msg, sizeof msg, "kernel id %d", kid);
+            fatal(__FILE__, __LINE__, "invalid kernel id in task array", msg);
+        }
+    }
+}
+
+// ---- launchers ---------------------------------------------------------------------------------------
+template <class K> void set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024)
+    {
+        if ((int)bytes > g.max_smem_optin) fatal(__FILE__, __LINE__, "block size nb needs more shared memory than the device offers; reduce init_options.nb", nullptr);
+        CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    }
+}
+
+struct Timer
+{
+    int cls;
+    bool on;
+    Timer(int c) : cls(c), on(g.opt.profile != 0) { if (on) CK(cudaEventRecord(g.ev0, g.stream)); }
+    ~Timer()
+    {
+        if (on)
+        {
+            CK(cudaEventRecord(g.ev1, g.stream));
+            CK(cudaEventSynchronize(g.ev1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
+            g.ms[cls] += ms;
+        }
+    }
+};
+
+template <int WARPS> void launch_ssssm_sparse_w(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
+{
+    const int groups = (nb + WARPS - 1) / WARPS;
+    const size_t smem = (size_t)WARPS * nb * sizeof(T);
+    set_smem(ssssm_sparse_kernel<T, WARPS>, smem);
+    // grid.x is limited to 2^31-1; batches stay far below (ndest * groups)
+    ssssm_sparse_kernel<T, WARPS><<<(unsigned)(ndest * groups), WARPS * PSM_WARP, smem, g.stream>>>(nb, d, p, groups);
+    CK_LAST();
+}
+void launch_ssssm_sparse(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
+{
+    if (!ndest) return;
+    Timer tm(K_SSSSM_SPARSE);
+    const size_t per_warp = (size_t)nb * sizeof(T);
+    if (8 * per_warp <= (size_t)g.max_smem_optin / 2) launch_ssssm_sparse_w<8>(nb, d, p, ndest);
+    else if (4 * per_warp <= (size_t)g.max_smem_optin) launch_ssssm_sparse_w<4>(nb, d, p, ndest);
+    else launch_ssssm_sparse_w<1>(nb, d, p, ndest);
+    g.launches[K_SSSSM_SPARSE]++;
+}
+
+template <int WARPS> void launch_panel_w(int nb, const PanelTask<T>* t, size_t n)
+{
+    const int groups = (nb + WARPS - 1) / WARPS;
+    const size_t smem = (size_t)WARPS * nb * sizeof(T);
+    set_smem(panel_solve_kernel<T, WARPS>, smem);
+    panel_solve_kernel<T, WARPS><<<(unsigned)(n * groups), WARPS * PSM_WARP, smem, g.stream>>>(nb, t, groups);
+    CK_LAST();
+}
+void launch_panel(int nb, const PanelTask<T>* t, size_t n)
+{
+    if (!n) return;
+    Timer tm(K_TSTRF);
+    const size_t per_warp = (size_t)nb * sizeof(T);
+    if (8 * per_warp <= (size_t)g.max_smem_optin / 2) launch_panel_w<8>(nb, t, n);
+    else if (4 * per_warp <= (size_t)g.max_smem_optin) launch_panel_w<4>(nb, t, n);
+    else launch_panel_w<1>(nb, t, n);
+    g.launches[K_TSTRF]++;
+}
+
+void launch_getrf(int nb, const GetrfTask<T>* t, size_t n)
+{
+    if (!n) return;
+    Timer tm(K_GETRF);
+    constexpr int THREADS = 512;
+    const size_t smem = (size_t)4 * nb * sizeof(T);
+    set_smem(getrf_sparse_kernel<T, THREADS>, smem);
+    getrf_sparse_kernel<T, THREADS><<<(unsigned)n, THREADS, smem, g.stream>>>(nb, t);
+    CK_LAST();
+    g.launches[K_GETRF]++;
+}
+
+void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t s1)
+{
+    for (size_t s = s0; s < s1; ++s)
+    {
+        const Step& st = P.steps[s];
+        switch (st.kind)
+        {
+        case K_SSSSM_SPARSE: launch_ssssm_sparse(nb, D.dests + st.off, D.pairs, st.count); break;
+        case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); break;
+        case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count); break;
+        case -1:
+            for (size_t k = st.off; k < st.off + st.count; ++k)
+                CK(cudaMemcpyAsync(P.downloads[k].h, P.downloads[k].d, P.downloads[k].bytes, cudaMemcpyDeviceToHost, g.stream));
+            g.launches[K_AUX] += (long long)st.count;
+            break;
+        default: fatal(__FILE__, __LINE__, "corrupt step list", nullptr);
+        }
+    }
+}
+
+template <class V> size_t vbytes(const V& v) { return (v.size() * sizeof(typename V::value_type) + 255) & ~(size_t)255; }
+
+// one-shot execution of a task array (the hybrid_batched / getrf / tstrf / ... entry points)
+void execute_tasks(int nb, size_t ntask, const pangulu_task_t* tasks)
+{
+    if (!ntask) return;
+    ensure_ctx();
+    Program P;
+    append_tasks(P, nb, tasks, 0, ntask, g.opt.eager_download != 0);
+    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs);
+    Slab& sl = take_slab(b0 + b1 + b2 + b3 + 256);
+    char* h = sl.h;
+    if (!P.getrf.empty()) memcpy(h, P.getrf.data(), P.getrf.size() * sizeof(GetrfTask<T>));
+    if (!P.panel.empty()) memcpy(h + b0, P.panel.data(), P.panel.size() * sizeof(PanelTask<T>));
+    if (!P.dests.empty()) memcpy(h + b0 + b1, P.dests.data(), P.dests.size() * sizeof(SsssmDest<T>));
+    if (!P.pairs.empty()) memcpy(h + b0 + b1 + b2, P.pairs.data(), P.pairs.size() * sizeof(SsssmPair<T>));
+    CK(cudaMemcpyAsync(sl.d, sl.h, b0 + b1 + b2 + b3, cudaMemcpyHostToDevice, g.stream));
+    DevProgram D;
+    D.getrf = (GetrfTask<T>*)sl.d;
+    D.panel = (PanelTask<T>*)(sl.d + b0);
+    D.dests = (SsssmDest<T>*)(sl.d + b0 + b1);
+    D.pairs = (SsssmPair<T>*)(sl.d + b0 + b1 + b2);
+    run_steps(nb, P, D, 0, P.steps.size());
+    CK(cudaEventRecord(sl.done, g.stream));
+}
+
+void single_task(int nb, int kernel_id, pangulu_storage_slot_t* opdst, pangulu_storage_slot_t* op1, pangulu_storage_slot_t* op2)
+{
+    pangulu_task_t t;
+    memset(&t, 0, sizeof t);
+    t.kernel_id = (pangulu_int16_t)kernel_id;
+    t.opdst = opdst;
+    t.op1 = op1;
+    t.op2 = op2;
+    t.row = opdst->brow_pos;
+    t.col = opdst->bcol_pos;
+    execute_tasks(nb, 1, &t);
+}
+
+}  // namespace
+
+// the plan type is visible to C callers only as an opaque pointer
+struct pangulu_sm100_plan
+{
+    int nb;
+    Program P;
+    DevProgram D;
+    std::vector<size_t> wave_step;  // wave w -> first step
+    void* dev_buf;
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------------
+// Part 1: PanguLU platform interface
+// ------------------------------------------------------------------------------------------------------
+void PSM(malloc)(void** platform_address, size_t size) { CK(cudaMalloc(platform_address, size)); }
+
+void PSM(malloc_pinned)(void** platform_address, size_t size) { CK(cudaHostAlloc(platform_address, size, cudaHostAllocDefault)); }
+
+void PSM(synchronize)(void) { CK(cudaDeviceSynchronize()); }
+
+void PSM(memset)(void* s, int c, size_t n) { CK(cudaMemset(s, c, n)); }
+
+void PSM(create_stream)(void** stream) { CK(cudaStreamCreate((cudaStream_t*)stream)); }
+
+static cudaMemcpyKind kind_of(unsigned int kind)
+{
+    switch (kind)
+    {
+    case 0: return cudaMemcpyHostToDevice;
+    case 1: return cudaMemcpyDeviceToHost;
+    case 2: return cudaMemcpyDeviceToDevice;
+    }
+    fprintf(stderr, "Invalid memcpy kind value\n");
+    exit(EXIT_FAILURE);
+}
+
+void PSM(memcpy)(void* dst, const void* src, size_t count, unsigned int kind) { CK(cudaMemcpy(dst, src, count, kind_of(kind))); }
+
+void PSM(memcpy_async)(void* dst, const void* src, size_t count, unsigned int kind, void* stream)
+{
+    CK(cudaMemcpyAsync(dst, src, count, kind_of(kind), (cudaStream_t)stream));
+}
+
+void PSM(free)(void* devptr) { CK(cudaFree(devptr)); }
+
+void PSM(get_device_num)(int* device_num) { CK(cudaGetDeviceCount(device_num)); }
+
+void PSM(set_default_device)(int device_num)
+{
+    CK(cudaSetDevice(device_num));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_num));
+    if (&pangulu_gpu_shared_mem_size) pangulu_gpu_shared_mem_size = (int)prop.sharedMemPerBlock;
+}
+
+void PSM(get_device_name)(char* name, int device_num)
+{
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_num));
+    strcpy(name, prop.name);
+}
+
+void PSM(get_device_memory_usage)(size_t* used_byte)
+{
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    *used_byte = total_b - free_b;
+}
+
+void PSM(getrf)(pangulu_inblock_idx nb, pangulu_storage_slot_t* opdst, int tid)
+{
+    (void)tid;
+    single_task(nb, PANGULU_TASK_GETRF, opdst, nullptr, nullptr);
+}
+
+void PSM(tstrf)(pangulu_inblock_idx nb, pangulu_storage_slot_t* opdst, pangulu_storage_slot_t* opdiag, int tid)
+{
+    (void)tid;
+    single_task(nb, PANGULU_TASK_TSTRF, opdst, opdiag, nullptr);
+}
+
+void PSM(gessm)(pangulu_inblock_idx nb, pangulu_storage_slot_t* opdst, pangulu_storage_slot_t* opdiag, int tid)
+{
+    (void)tid;
+    single_task(nb, PANGULU_TASK_GESSM, opdst, opdiag, nullptr);
+}
+
+void PSM(ssssm)(pangulu_inblock_idx nb, pangulu_storage_slot_t* opdst, pangulu_storage_slot_t* op1, pangulu_storage_slot_t* op2, int tid)
+{
+    (void)tid;
+    single_task(nb, PANGULU_TASK_SSSSM, opdst, op1, op2);
+}
+
+void PSM(ssssm_batched)(pangulu_inblock_idx nb, pangulu_uint64_t ntask, pangulu_task_t* tasks)
+{
+    for (pangulu_uint64_t i = 0; i < ntask; ++i)
+        if (tasks[i].kernel_id != PANGULU_TASK_SSSSM) tasks[i].kernel_id = PANGULU_TASK_SSSSM;  // the reference treats every entry as SSSSM (…0201000.cu:900-909)
+    execute_tasks(nb, ntask, tasks);
+}
+
+void PSM(hybrid_batched)(pangulu_inblock_idx nb, pangulu_uint64_t ntask, pangulu_task_t* tasks) { execute_tasks(nb, ntask, tasks); }
+
+void PSM(spmv)(pangulu_inblock_idx nb, pangulu_storage_slot_t* a, calculate_type* x, calculate_type* y)
+{
+    ensure_ctx();
+    Blk<T> A = blk_csc(a);
+    const int threads = 256;
+    const int blocks = (nb * PSM_WARP + threads - 1) / threads;
+    spmv_kernel<T><<<blocks, threads, 0, g.stream>>>(nb, A, (const T*)x, (T*)y);
+    CK_LAST();
+    g.launches[K_AUX]++;
+}
+
+void PSM(vecadd)(pangulu_int64_t length, calculate_type* bval, calculate_type* xval)
+{
+    ensure_ctx();
+    if (length <= 0) return;
+    vecadd_kernel<T><<<(unsigned)((length + 255) / 256), 256, 0, g.stream>>>(length, (T*)bval, (const T*)xval);
+    CK_LAST();
+    g.launches[K_AUX]++;
+}
+
+void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t* s, calculate_type* xval, pangulu_int64_t uplo)
+{
+    ensure_ctx();
+    // uplo 0: s is a lower half / strictly-lower pattern in CSC; uplo 1: s is the UPPER half of a diagonal block
+    Blk<T> S = uplo == 0 ? blk_csc(s) : blk_upper_diag(s);
+    constexpr int THREADS = 256;
+    const size_t smem = (size_t)nb * sizeof(T);
+    set_smem(sptrsv_kernel<T, THREADS>, smem);
+    sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, S, (T*)xval, (int)uplo);
+    CK_LAST();
+    g.launches[K_AUX]++;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Part 2: additive entry points
+// ------------------------------------------------------------------------------------------------------
+static long long* option_slot(const char* key)
+{
+    if (!key) return nullptr;
+    if (!strcmp(key, "eager_download")) return &g.opt.eager_download;
+    if (!strcmp(key, "dense_threshold")) return &g.opt.dense_threshold;
+    if (!strcmp(key, "ssssm_mode")) return &g.opt.ssssm_mode;
+    if (!strcmp(key, "profile")) return &g.opt.profile;
+    return nullptr;
+}
+int pangulu_sm100_set_option(const char* key, long long value)
+{
+    long long* p = option_slot(key);
+    if (!p) return -1;
+    *p = value;
+    return 0;
+}
+long long pangulu_sm100_get_option(const char* key)
+{
+    long long* p = option_slot(key);
+    return p ? *p : -1;
+}
+
+void pangulu_sm100_free_pinned(void* host_ptr) { if (host_ptr) CK(cudaFreeHost(host_ptr)); }
+
+void pangulu_sm100_download_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t** slots)
+{
+    ensure_ctx();
+    for (pangulu_uint64_t i = 0; i < n; ++i)
+        CK(cudaMemcpyAsync(slots[i]->value, slots[i]->d_value, sizeof(T) * (size_t)slot_nnz(nb, slots[i]), cudaMemcpyDeviceToHost, g.stream));
+    g.launches[K_AUX] += (long long)n;
+}
+
+void pangulu_sm100_upload_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t** slots)
+{
+    ensure_ctx();
+    for (pangulu_uint64_t i = 0; i < n; ++i)
+        CK(cudaMemcpyAsync(slots[i]->d_value, slots[i]->value, sizeof(T) * (size_t)slot_nnz(nb, slots[i]), cudaMemcpyHostToDevice, g.stream));
+    g.launches[K_AUX] += (long long)n;
+}
+
+pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_uint64_t nwave, const pangulu_uint64_t* waves,
+                                              const pangulu_task_t* tasks)
+{
+    ensure_ctx();
+    pangulu_sm100_plan* pl = new pangulu_sm100_plan();
+    pl->nb = nb;
+    pl->dev_buf = nullptr;
+    for (pangulu_uint64_t w = 0; w < nwave; ++w)
+    {
+        pl->wave_step.push_back(pl->P.steps.size());
+        append_tasks(pl->P, nb, tasks, waves[w], waves[w + 1], false);
+    }
+    pl->wave_step.push_back(pl->P.steps.size());
+    Program& P = pl->P;
+    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs);
+    char* d = nullptr;
+    CK(cudaMalloc((void**)&d, b0 + b1 + b2 + b3 + 256));
+    pl->dev_buf = d;
+    if (!P.getrf.empty()) CK(cudaMemcpy(d, P.getrf.data(), P.getrf.size() * sizeof(GetrfTask<T>), cudaMemcpyHostToDevice));
+    if (!P.panel.empty()) CK(cudaMemcpy(d + b0, P.panel.data(), P.panel.size() * sizeof(PanelTask<T>), cudaMemcpyHostToDevice));
+    if (!P.dests.empty()) CK(cudaMemcpy(d + b0 + b1, P.dests.data(), P.dests.size() * sizeof(SsssmDest<T>), cudaMemcpyHostToDevice));
+    if (!P.pairs.empty()) CK(cudaMemcpy(d + b0 + b1 + b2, P.pairs.data(), P.pairs.size() * sizeof(SsssmPair<T>), cudaMemcpyHostToDevice));
+    pl->D.getrf = (GetrfTask<T>*)d;
+    pl->D.panel = (PanelTask<T>*)(d + b0);
+    pl->D.dests = (SsssmDest<T>*)(d + b0 + b1);
+    pl->D.pairs = (SsssmPair<T>*)(d + b0 + b1 + b2);
+    // the host copies of the descriptor arrays are no longer needed; keep only the step list
+    std::vector<GetrfTask<T>>().swap(P.getrf);
+    std::vector<PanelTask<T>>().swap(P.panel);
+    std::vector<SsssmDest<T>>().swap(P.dests);
+    std::vector<SsssmPair<T>>().swap(P.pairs);
+    return pl;
+}
+
+void pangulu_sm100_plan_execute_range(pangulu_sm100_plan* pl, pangulu_uint64_t w0, pangulu_uint64_t w1)
+{
+    if (!pl) fatal(__FILE__, __LINE__, "null plan", nullptr);
+    const size_t nw = pl->wave_step.size() - 1;
+    if (w1 > nw) w1 = nw;
+    if (w0 >= w1) return;
+    run_steps(pl->nb, pl->P, pl->D, pl->wave_step[w0], pl->wave_step[w1]);
+}
+
+void pangulu_sm100_plan_execute(pangulu_sm100_plan* pl) { pangulu_sm100_plan_execute_range(pl, 0, pl ? pl->wave_step.size() - 1 : 0); }
+
+void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
+{
+    if (!pl) return;
+    if (pl->dev_buf) CK(cudaFree(pl->dev_buf));
+    delete pl;
+}
+
+void pangulu_sm100_stats_reset(void)
+{
+    for (int i = 0; i < K_NCLASS; ++i) { g.launches[i] = 0; g.ms[i] = 0; }
+}
+long long pangulu_sm100_stats_launches(int cls) { return (cls >= 0 && cls < K_NCLASS) ? g.launches[cls] : -1; }
+double pangulu_sm100_stats_ms(int cls) { return (cls >= 0 && cls < K_NCLASS) ? g.ms[cls] : -1.0; }
+void* pangulu_sm100_stream(void) { ensure_ctx(); return (void*)g.stream; }
+
+const char* pangulu_sm100_version(void)
+{
+#if defined(CALCULATE_TYPE_CR64)
+    return "pangulu-sm100 cr64 id=" PSM_STR(PANGULU_SM100_ID) " sm_100a";
+#elif defined(CALCULATE_TYPE_CR32)
+    return "pangulu-sm100 cr32 id=" PSM_STR(PANGULU_SM100_ID) " sm_100a";
+#elif defined(CALCULATE_TYPE_R32)
+    return "pangulu-sm100 r32 id=" PSM_STR(PANGULU_SM100_ID) " sm_100a";
+#else
+    return "pangulu-sm100 r64 id=" PSM_STR(PANGULU_SM100_ID) " sm_100a";
+#endif
+}
+
+}  // extern "C"

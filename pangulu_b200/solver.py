@@ -1,0 +1,159 @@
+"""Python face of the host driver: the reference's five-call API (include/pangulu.h:11-15) as a class.
+
+    s = PanguLU(A_csc, nb=256)      # pangulu_init  (reorder, symbolic, blocks, schedule, device mirror)
+    s.gstrf()                        # pangulu_gstrf (numeric LU on the GPU through the platform C ABI)
+    x = s.gstrs(b)                   # pangulu_gstrs
+    s.finalize()                     # pangulu_finalize
+
+All arithmetic of the factorisation happens in the CUDA extension; this file only marshals arrays.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+
+DTYPE_TO_VTYPE = {np.dtype(np.float64): "r64", np.dtype(np.float32): "r32",
+                  np.dtype(np.complex128): "cr64", np.dtype(np.complex64): "cr32"}
+
+
+@dataclass
+class Block:
+    """Host view of one block slot (arrays alias the driver's pinned buffer unless copied)."""
+    brow: int
+    bcol: int
+    is_upper: int
+    owned: bool
+    colptr: np.ndarray
+    rowidx: np.ndarray
+    value: np.ndarray
+    rowptr: np.ndarray | None = None
+    colidx: np.ndarray | None = None
+    csr2csc: np.ndarray | None = None
+
+
+def _as_array(ptr, count, dtype):
+    if not ptr or count == 0:
+        return np.zeros(0, dtype=dtype)
+    buf = (C.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=count)
+
+
+def driver_config(vtype: str = "r64", **kw) -> None:
+    """Set driver options (include/pangulu_sm100_driver.h) before constructing a solver."""
+    L = _lib.load(vtype)
+    for k, v in kw.items():
+        if L.pangulu_sm100_driver_config(k.encode(), int(v)) != 0:
+            raise KeyError(k)
+
+
+class PanguLU:
+    def __init__(self, A, nb: int = 256, *, ordering: int = -1, mode: int = 0, rank: int = 0, nproc: int = 1,
+                 host_only: bool = False, nthread: int = 1, verbose: bool = False):
+        """A: scipy.sparse matrix (any format; converted to sorted CSC) of dtype f64/f32/c128/c64."""
+        import scipy.sparse as sp
+
+        A = sp.csc_matrix(A)
+        A.sort_indices()
+        self.dtype = np.dtype(A.dtype)
+        if self.dtype not in DTYPE_TO_VTYPE:
+            raise TypeError(f"unsupported value type {self.dtype}")
+        self.vtype = DTYPE_TO_VTYPE[self.dtype]
+        self.L = _lib.load(self.vtype)
+        self.n = A.shape[0]
+        driver_config(self.vtype, ordering=ordering, mode=mode, rank=rank, nproc=nproc, host_only=int(host_only),
+                      verbose=int(verbose))
+        self._colptr = np.ascontiguousarray(A.indptr, dtype=np.uint64)
+        self._rowidx = np.ascontiguousarray(A.indices, dtype=np.uint32)
+        self._value = np.ascontiguousarray(A.data, dtype=self.dtype)
+        opt = _lib.InitOptions(nthread=nthread, nb=nb, gpu_kernel_warp_per_block=4, gpu_data_move_warp_per_block=4,
+                               sizeof_value=self.dtype.itemsize, is_complex_matrix=int(self.dtype.kind == "c"),
+                               mpi_recv_buffer_level=0.5)
+        self._h = C.c_void_p()
+        self.L.pangulu_init(self.n, int(self._colptr[-1]), self._colptr.ctypes.data, self._rowidx.ctypes.data,
+                            self._value.ctypes.data, C.byref(opt), C.byref(self._h))
+        self.nb = int(self.info("nb"))
+
+    # -- reference API -----------------------------------------------------------------------------
+    def gstrf(self) -> float:
+        opt = C.c_char(0)
+        self.L.pangulu_gstrf(C.byref(opt), C.byref(self._h))
+        return self.info("time_gstrf")
+
+    def gstrs(self, rhs: np.ndarray) -> np.ndarray:
+        x = np.array(rhs, dtype=self.dtype, copy=True)
+        opt = C.c_char(0)
+        self.L.pangulu_gstrs(x.ctypes.data, C.byref(opt), C.byref(self._h))
+        return x
+
+    def gssv(self, rhs: np.ndarray) -> np.ndarray:
+        self.gstrf()
+        return self.gstrs(rhs)
+
+    def finalize(self) -> None:
+        if self._h:
+            self.L.pangulu_finalize(C.byref(self._h))
+            self._h = C.c_void_p()
+
+    # -- driver extras ------------------------------------------------------------------------------
+    def info(self, key: str) -> float:
+        return float(self.L.pangulu_sm100_driver_info(self._h, key.encode()))
+
+    def reset_values(self, also_device: bool = True) -> None:
+        self.L.pangulu_sm100_driver_reset_values(self._h, int(also_device))
+
+    def download(self) -> None:
+        self.L.pangulu_sm100_driver_download(self._h)
+
+    def factor_check(self) -> float:
+        return float(self.L.pangulu_sm100_driver_factor_check(self._h))
+
+    def perms(self) -> dict:
+        n = self.n
+        g = lambda w, dt: _as_array(self.L.pangulu_sm100_driver_perm(self._h, w), n, dt).copy()
+        return {"row_perm": g(0, np.uint32), "col_perm": g(1, np.uint32), "metis_perm": g(2, np.uint32),
+                "row_scale": g(3, self.dtype), "col_scale": g(4, self.dtype)}
+
+    def slot_ptr(self, i: int):
+        return self.L.pangulu_sm100_driver_slot(self._h, i)
+
+    def blocks(self, copy: bool = True, owned_only: bool = True) -> list[Block]:
+        nb = self.nb
+        out = []
+        for i in range(int(self.info("num_slots"))):
+            s = self.slot_ptr(i).contents
+            owned = s.bin_id == 0
+            if owned_only and not owned:
+                continue
+            cp = _as_array(s.columnpointer, nb + 1, np.uint32)
+            nnz = int(cp[nb])
+            arr = lambda p, cnt, dt: (_as_array(p, cnt, dt).copy() if copy else _as_array(p, cnt, dt))
+            b = Block(s.brow_pos, s.bcol_pos, s.is_upper, owned, arr(s.columnpointer, nb + 1, np.uint32),
+                      arr(s.rowindex, nnz, np.uint16), arr(s.value, nnz, self.dtype))
+            if s.brow_pos > s.bcol_pos:
+                b.rowptr = arr(s.rowpointer, nb + 1, np.uint32)
+                b.colidx = arr(s.columnindex, nnz, np.uint16)
+                b.csr2csc = arr(s.idx_of_csc_value_for_csr, nnz, np.uint32)
+            out.append(b)
+        return out
+
+    def schedule(self):
+        """(tasks as a numpy structured view, wave_ptr)."""
+        wp = C.c_void_p()
+        tp = self.L.pangulu_sm100_driver_tasks(self._h, C.byref(wp))
+        nwave, ntask = int(self.info("nwave")), int(self.info("ntask"))
+        wave_ptr = _as_array(wp.value, nwave + 1, np.uint64).copy()
+        dt = np.dtype({"names": ["row", "col", "kernel_id", "task_level", "compare_flag", "opdst", "op1", "op2"],
+                       "formats": [np.uint32, np.uint32, np.int16, np.uint32, np.int64, np.uint64, np.uint64, np.uint64],
+                       "offsets": [0, 4, 8, 12, 16, 24, 32, 40], "itemsize": 48})
+        tasks = _as_array(tp, ntask, dt) if ntask else np.zeros(0, dtype=dt)
+        return tasks, wave_ptr
+
+    def __del__(self):
+        try:
+            self.finalize()
+        except Exception:
+            pass
