@@ -1,0 +1,124 @@
+"""Run the unmodified reference (oracle/_ref) on one matrix in a FRESH process and save what it produced.
+
+The reference keeps process-global state and cannot be initialised twice in one process, so every
+factorisation gets its own interpreter:
+
+    python -m oracle.ref_run in.npz out.npz --nb 64 [--vtype r64] [--perf] [--no-solve] [--no-blocks]
+
+in.npz : indptr, indices, data, n (CSC).  out.npz: perms, blocks before/after gstrf (flattened), x, times,
+flop.  TEST INFRASTRUCTURE ONLY (tests/, smoke(), bench.py cpu_baseline / --impl reference).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+
+
+def _flatten(blocks, prefix, out):
+    out[prefix + "meta"] = np.array([[b.brow, b.bcol, b.is_upper, len(b.value)] for b in blocks], dtype=np.int64).reshape(-1, 4)
+    out[prefix + "colptr"] = np.concatenate([b.colptr for b in blocks]) if blocks else np.zeros(0, np.uint32)
+    out[prefix + "rowidx"] = np.concatenate([b.rowidx for b in blocks]) if blocks else np.zeros(0, np.uint16)
+    out[prefix + "value"] = np.concatenate([b.value for b in blocks]) if blocks else np.zeros(0)
+
+
+def unflatten(z, prefix, nb):
+    """Inverse of _flatten: list of simple block objects (CSR mirrors rebuilt on demand by the caller)."""
+    from types import SimpleNamespace
+
+    meta = z[prefix + "meta"]
+    colptr, rowidx, value = z[prefix + "colptr"], z[prefix + "rowidx"], z[prefix + "value"]
+    out, o = [], 0
+    for i, (brow, bcol, is_upper, nnz) in enumerate(meta):
+        b = SimpleNamespace(brow=int(brow), bcol=int(bcol), is_upper=int(is_upper),
+                            colptr=np.ascontiguousarray(colptr[i * (nb + 1):(i + 1) * (nb + 1)]),
+                            rowidx=np.ascontiguousarray(rowidx[o:o + nnz]), value=np.ascontiguousarray(value[o:o + nnz]),
+                            rowptr=None, colidx=None, csr2csc=None)
+        o += int(nnz)
+        out.append(b)
+    return out
+
+
+def add_csr_mirror(b, nb):
+    """rowptr/colidx/csr2csc of a CSC block (same result as pangulu_transpose_struct_with_valueidx_inblock)."""
+    nnz = int(b.colptr[nb])
+    cols = np.repeat(np.arange(nb, dtype=np.uint16), np.diff(b.colptr.astype(np.int64)))
+    order = np.lexsort((cols, b.rowidx[:nnz]))
+    b.colidx = np.ascontiguousarray(cols[order])
+    b.csr2csc = np.ascontiguousarray(order.astype(np.uint32))
+    cnt = np.bincount(b.rowidx[:nnz], minlength=nb)
+    b.rowptr = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint32)
+    return b
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("inp")
+    ap.add_argument("out")
+    ap.add_argument("--nb", type=int, required=True)
+    ap.add_argument("--vtype", default="r64")
+    ap.add_argument("--perf", action="store_true")
+    ap.add_argument("--no-solve", action="store_true")
+    ap.add_argument("--no-blocks", action="store_true")
+    ap.add_argument("--nthread", type=int, default=1)
+    a = ap.parse_args(argv)
+    sys.path.insert(0, _ROOT)
+    from oracle.ref import RefLib
+
+    z = np.load(a.inp)
+    n = int(z["n"])
+    R = RefLib(a.vtype, perf=a.perf)
+    f = R.factor(n, z["indptr"], z["indices"], z["data"], a.nb, nthread=a.nthread)
+    out = {"n": n, "nb": f.nb, "symbolic_nnz": f.symbolic_nnz, "has_metis": int(R.has_metis), "has_mc64": int(R.has_mc64)}
+    out.update(f.perms())
+    if not a.no_blocks:
+        _flatten(f.blocks(), "pre_", out)
+    t = f.gstrf()
+    out["t_gstrf"] = t
+    out["flop"] = f.flop()
+    out["blas"] = R.blas_backend
+    if not a.no_blocks:
+        _flatten(f.blocks(), "post_", out)
+    if not a.no_solve:
+        import scipy.sparse as sp
+
+        A = sp.csc_matrix((z["data"], z["indices"], z["indptr"]), shape=(n, n))
+        b = A @ np.ones(n, dtype=A.dtype)
+        x = f.gstrs(b)
+        out["x"] = x
+        out["resid"] = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+    np.savez(a.out, **out)
+
+
+def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthread=1, quiet=True):
+    """Factor scipy CSC matrix A with the reference in a subprocess; returns the loaded npz dict."""
+    import scipy.sparse as sp
+
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    with tempfile.TemporaryDirectory() as td:
+        inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
+        np.savez(inp, indptr=A.indptr.astype(np.uint64), indices=A.indices.astype(np.uint32), data=A.data, n=A.shape[0])
+        cmd = [sys.executable, "-m", "oracle.ref_run", inp, out, "--nb", str(nb), "--vtype", vtype, "--nthread", str(nthread)]
+        if perf:
+            cmd.append("--perf")
+        if not solve:
+            cmd.append("--no-solve")
+        if not blocks:
+            cmd.append("--no-blocks")
+        r = subprocess.run(cmd, cwd=_ROOT, stdout=subprocess.PIPE if quiet else None, stderr=subprocess.STDOUT if quiet else None)
+        if r.returncode != 0:
+            raise RuntimeError("reference run failed:\n" + (r.stdout.decode(errors="replace") if r.stdout else ""))
+        with np.load(out, allow_pickle=False) as z:
+            return {k: z[k] for k in z.files}
+
+
+if __name__ == "__main__":
+    main()

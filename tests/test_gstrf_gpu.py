@@ -1,0 +1,124 @@
+"""Whole-factorisation parity on the GPU through the reference-shaped API
+(pangulu_init -> pangulu_gstrf -> pangulu_gstrs of include/pangulu_sm100_driver.h).
+
+Gates (north star): nonzero structure and permutation indices bit-exact, L/U values within 1e-12
+(R64/CR64) / 1e-5 (R32/CR32) block-wise relative, solve residual no worse than the reference's.
+The expected factors come from the unmodified reference run in a subprocess (oracle/_ref, prebuilt) when it
+is present, otherwise from the C oracle's block LU (oracle/pangulu_oracle.c).
+"""
+import copy
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+from helpers import TOL, rel_err, trefethen_matrix
+from pangulu_b200 import PanguLU, _lib, matrices
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("trefethen-nb4", lambda: trefethen_matrix(), 4),
+    ("trefethen-nb10", lambda: trefethen_matrix(), 10),
+    ("trefethen-nb19", lambda: trefethen_matrix(), 19),
+    ("laplace2d-40-nb32", lambda: matrices.laplace2d(40), 32),
+    ("poisson3d-12-nb64", lambda: matrices.poisson3d(12), 64),
+    ("stencil27-8-nb64", lambda: matrices.stencil27(8), 64),
+    ("poisson3d-16-nb256", lambda: matrices.poisson3d(16), 256),
+]
+
+
+def _expected(A, nb, vtype):
+    """(blocks after gstrf, metis_perm or None, residual or None) from the reference, else the C oracle."""
+    from oracle.ref import ref_available
+
+    if ref_available(vtype):
+        from oracle.ref_run import run_reference, unflatten
+
+        z = run_reference(A, nb, vtype=vtype)
+        return unflatten(z, "post_", nb), z["metis_perm"], float(z["resid"])
+    from oracle.oracle import Oracle
+
+    s = PanguLU(A, nb=nb, host_only=True)
+    blocks = [SimpleNamespace(**vars(b)) for b in s.blocks(copy=True)]
+    s.finalize()
+    Oracle(vtype).block_lu(nb, blocks)
+    return blocks, None, None
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["abi-host-buffers", "resident-plan"])
+@pytest.mark.parametrize("name,make,nb", CASES, ids=[c[0] for c in CASES])
+def test_gstrf_r64(name, make, nb, mode):
+    A = make().astype(np.float64)
+    n = A.shape[0]
+    want, metis_perm, ref_resid = _expected(A, nb, "r64")
+    s = PanguLU(A, nb=nb, mode=mode)
+    try:
+        s.gstrf()
+        if mode == 1:
+            s.download()
+        got = s.blocks(copy=True)
+        assert len(got) == len(want)
+        if metis_perm is not None:
+            assert np.array_equal(s.perms()["metis_perm"], metis_perm)
+        worst = 0.0
+        for g, w in zip(got, want):
+            assert (g.brow, g.bcol, g.is_upper) == (w.brow, w.bcol, w.is_upper)
+            assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)  # structure: bit-exact
+            worst = max(worst, rel_err(g.value, w.value))
+        assert worst <= TOL["r64"], f"L/U values differ by {worst:.3e}"
+        assert s.factor_check() < 1e-12
+        b = A @ np.ones(n)
+        x = s.gstrs(b)
+        resid = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+        bound = 1e-13 if ref_resid is None else max(4.0 * ref_resid, 1e-15)
+        assert resid <= bound, f"residual {resid:.3e} vs reference {ref_resid}"
+    finally:
+        s.finalize()
+
+
+@pytest.mark.parametrize("vtype", ["r32", "cr64", "cr32"])
+def test_gstrf_other_types(vtype):
+    dtype = _lib.VALUE_DTYPES[vtype]
+    nb = 32
+    if np.dtype(dtype).kind == "c":
+        A = matrices.circuit_like(600, seed=11, dmax=20, dtype=dtype)
+    else:
+        A = matrices.poisson3d(10).astype(dtype)
+    n = A.shape[0]
+    want, metis_perm, ref_resid = _expected(A, nb, vtype)
+    s = PanguLU(A, nb=nb, mode=0)
+    try:
+        s.gstrf()
+        got = s.blocks(copy=True)
+        assert len(got) == len(want)
+        worst = 0.0
+        for g, w in zip(got, want):
+            assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)
+            worst = max(worst, rel_err(g.value, w.value))
+        assert worst <= TOL[vtype] * 10, f"L/U values differ by {worst:.3e}"
+        b = (A @ np.ones(n, dtype=dtype)).astype(dtype)
+        x = s.gstrs(b)
+        resid = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+        assert resid <= (1e-4 if "32" in vtype else 1e-12)
+    finally:
+        s.finalize()
+
+
+def test_refactor_after_reset():
+    """gstrf twice on one handle (values reset in between) gives the same factors: idempotence of the
+    reset + factor cycle used by bench.py."""
+    A = matrices.poisson3d(10)
+    s = PanguLU(A, nb=32, mode=1)
+    try:
+        s.gstrf()
+        s.download()
+        first = [b.value.copy() for b in s.blocks(copy=True)]
+        s.reset_values(True)
+        s.gstrf()
+        s.download()
+        second = [b.value for b in s.blocks(copy=True)]
+        for a, b in zip(first, second):
+            assert rel_err(a, b) <= 1e-13
+    finally:
+        s.finalize()
