@@ -212,23 +212,41 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             size_t j = i;
             while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_SSSSM) ++j;
             // group by destination (a diagonal destination is identified by its LOWER half), keeping
-            // the array order of the updates of one destination
-            order.resize(j - i);
-            for (size_t k = 0; k < j - i; ++k) order[k] = i + k;
+            // the array order of the updates of one destination; inside a destination the operand pairs
+            // that go to the dense-tile kernel come first
+            const size_t nrun = j - i;
+            order.resize(nrun);
+            std::vector<char> cls(nrun);
+            const int mode = (int)g.opt.ssssm_mode;
+            const bool tile_ok = nb >= 32 && nb <= 256 && mode != 1;
+            const double thr = (double)g.opt.dense_threshold / 1000.0;
+            const double nb4thr2 = thr * thr * (double)nb * nb * (double)nb * nb;
+            for (size_t k = 0; k < nrun; ++k)
+            {
+                order[k] = k;
+                const pangulu_task_t& t = tasks[i + k];
+                const double na = slot_nnz(nb, t.op1), nbn = slot_nnz(nb, t.op2);
+                cls[k] = (tile_ok && (mode == 2 || na * nbn >= nb4thr2)) ? 0 : 1;
+            }
             auto key = [&](size_t k) -> const void* {
-                pangulu_storage_slot_t* d = tasks[k].opdst;
+                pangulu_storage_slot_t* d = tasks[i + k].opdst;
                 if (d->brow_pos == d->bcol_pos && d->is_upper) return d->related_block;
                 return d;
             };
-            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return key(a) < key(b); });
-            Step st; st.kind = K_SSSSM_SPARSE; st.off = P.dests.size(); st.count = 0;
+            std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+                const void *ka = key(a), *kb = key(b);
+                return ka != kb ? ka < kb : cls[a] < cls[b];
+            });
+            std::vector<SsssmDest<T>> by_cls[2];
             const void* cur = nullptr;
+            int cur_cls = -1;
             for (size_t k : order)
             {
-                const pangulu_task_t& t = tasks[k];
-                if (key(k) != cur)
+                const pangulu_task_t& t = tasks[i + k];
+                if (key(k) != cur || cls[k] != cur_cls)
                 {
                     cur = key(k);
+                    cur_cls = cls[k];
                     SsssmDest<T> D;
                     memset(&D, 0, sizeof D);
                     pangulu_storage_slot_t* d = t.opdst;
@@ -248,16 +266,28 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                     }
                     D.pair_begin = (u32)P.pairs.size();
                     D.pair_end = D.pair_begin;
-                    P.dests.push_back(D);
-                    st.count++;
+                    by_cls[cur_cls].push_back(D);
                 }
                 SsssmPair<T> pr;
                 pr.a = blk_ro(t.op1);
                 pr.b = blk_ro(t.op2);
                 P.pairs.push_back(pr);
-                P.dests.back().pair_end = (u32)P.pairs.size();
+                by_cls[cur_cls].back().pair_end = (u32)P.pairs.size();
             }
-            P.steps.push_back(st);
+            for (int c = 0; c < 2; ++c)
+            {
+                if (by_cls[c].empty()) continue;
+                // heaviest destinations first: the grid is consumed in order, this trims the tail
+                std::stable_sort(by_cls[c].begin(), by_cls[c].end(), [](const SsssmDest<T>& x, const SsssmDest<T>& y) {
+                    return (x.pair_end - x.pair_begin) > (y.pair_end - y.pair_begin);
+                });
+                Step st;
+                st.kind = c == 0 ? K_SSSSM_TILE : K_SSSSM_SPARSE;
+                st.off = P.dests.size();
+                st.count = by_cls[c].size();
+                P.dests.insert(P.dests.end(), by_cls[c].begin(), by_cls[c].end());
+                P.steps.push_back(st);
+            }
             i = j;
         }
         else if (kid == PANGULU_TASK_GETRF)
@@ -341,21 +371,43 @@ template <class K> void set_smem(K kernel, size_t bytes)
     }
 }
 
+// Per-launch device time (option "profile"): two events around every launch, recorded on the module's
+// stream and NOT synchronised here -- they are resolved when the statistics are read, so profiling does
+// not serialise host and device.
+struct EvPair { cudaEvent_t a, b; int cls; };
+std::vector<EvPair> g_pending;
+std::vector<cudaEvent_t> g_free_events;
+cudaEvent_t get_event()
+{
+    if (!g_free_events.empty()) { cudaEvent_t e = g_free_events.back(); g_free_events.pop_back(); return e; }
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    return e;
+}
+void resolve_timers()
+{
+    for (auto& p : g_pending)
+    {
+        CK(cudaEventSynchronize(p.b));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, p.a, p.b));
+        g.ms[p.cls] += ms;
+        g_free_events.push_back(p.a);
+        g_free_events.push_back(p.b);
+    }
+    g_pending.clear();
+}
 struct Timer
 {
-    int cls;
+    EvPair p;
     bool on;
-    Timer(int c) : cls(c), on(g.opt.profile != 0) { if (on) CK(cudaEventRecord(g.ev0, g.stream)); }
+    Timer(int c) : on(g.opt.profile != 0)
+    {
+        if (on) { p.cls = c; p.a = get_event(); p.b = get_event(); CK(cudaEventRecord(p.a, g.stream)); }
+    }
     ~Timer()
     {
-        if (on)
-        {
-            CK(cudaEventRecord(g.ev1, g.stream));
-            CK(cudaEventSynchronize(g.ev1));
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, g.ev0, g.ev1));
-            g.ms[cls] += ms;
-        }
+        if (on) { CK(cudaEventRecord(p.b, g.stream)); g_pending.push_back(p); }
     }
 };
 
@@ -377,6 +429,25 @@ void launch_ssssm_sparse(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, s
     else if (4 * per_warp <= (size_t)g.max_smem_optin) launch_ssssm_sparse_w<4>(nb, d, p, ndest);
     else launch_ssssm_sparse_w<1>(nb, d, p, ndest);
     g.launches[K_SSSSM_SPARSE]++;
+}
+
+template <int TM> void launch_ssssm_tile_t(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
+{
+    const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
+    const size_t a = (size_t)2 * PSM_TILE_K * (TM + 4 + PSM_TILE_N + 4), c = (size_t)PSM_TILE_N * (TM + 4);
+    const size_t smem = std::max(a, c) * sizeof(T);
+    set_smem(ssssm_tile_kernel<T, TM>, smem);
+    ssssm_tile_kernel<T, TM><<<(unsigned)(ndest * tiles), 256, smem, g.stream>>>(nb, d, p, tiles);
+    CK_LAST();
+}
+void launch_ssssm_tile(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
+{
+    if (!ndest) return;
+    Timer tm(K_SSSSM_TILE);
+    if (nb <= 64) launch_ssssm_tile_t<64>(nb, d, p, ndest);
+    else if (nb <= 128) launch_ssssm_tile_t<128>(nb, d, p, ndest);
+    else launch_ssssm_tile_t<256>(nb, d, p, ndest);
+    g.launches[K_SSSSM_TILE]++;
 }
 
 template <int WARPS> void launch_panel_w(int nb, const PanelTask<T>* t, size_t n)
@@ -418,6 +489,7 @@ void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t 
         switch (st.kind)
         {
         case K_SSSSM_SPARSE: launch_ssssm_sparse(nb, D.dests + st.off, D.pairs, st.count); break;
+        case K_SSSSM_TILE: launch_ssssm_tile(nb, D.dests + st.off, D.pairs, st.count); break;
         case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); break;
         case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count); break;
         case -1:
@@ -704,10 +776,15 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
 
 void pangulu_sm100_stats_reset(void)
 {
+    resolve_timers();
     for (int i = 0; i < K_NCLASS; ++i) { g.launches[i] = 0; g.ms[i] = 0; }
 }
 long long pangulu_sm100_stats_launches(int cls) { return (cls >= 0 && cls < K_NCLASS) ? g.launches[cls] : -1; }
-double pangulu_sm100_stats_ms(int cls) { return (cls >= 0 && cls < K_NCLASS) ? g.ms[cls] : -1.0; }
+double pangulu_sm100_stats_ms(int cls)
+{
+    resolve_timers();
+    return (cls >= 0 && cls < K_NCLASS) ? g.ms[cls] : -1.0;
+}
 void* pangulu_sm100_stream(void) { ensure_ctx(); return (void*)g.stream; }
 
 const char* pangulu_sm100_version(void)

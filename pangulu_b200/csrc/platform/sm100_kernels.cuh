@@ -342,4 +342,212 @@ __global__ void __launch_bounds__(THREADS) sptrsv_kernel(int nb, Blk<T> S, T* __
     for (int i = threadIdx.x; i < nb; i += THREADS) xg[i] = x[i];
 }
 
+// ================================================================================================
+// SSSSM, dense-tile path ("promoted" blocks: the only genuinely dense contraction of the factorisation).
+//
+// One CTA owns a TM x 32 tile of the destination (all rows of the block, 32 columns) and keeps it as
+// an FP64 accumulator in registers across EVERY operand pair queued for that destination.  Per pair
+// the k dimension is swept in chunks of 16: the 16 columns of A and the 16 x 32 piece of B are
+// scattered from their CSC arrays into zero-filled shared-memory tiles (k-major, row stride TM+4 /
+// 36 doubles = conflict-free for both the scatter and the fragment loads) and multiplied with
+// DMMA.8x8x4 (mma.sync.m8n8k4.f64 -- the FP64 tensor-core instruction of sm_100a; FP32 uses an FFMA
+// register tile on the same shared-memory layout, no TF32).  Chunks whose A columns are all empty
+// are skipped.  The epilogue spills the accumulator through shared memory and subtracts it from the
+// destination's CSC entries (and, for a diagonal destination, from the upper CSR half), so the
+// nonzero pattern stays untouched.  Double-buffered tiles, two block barriers per chunk.
+//   smem = max(2 * 16 * (TM+4 + 36), 32 * (TM+4)) * sizeof(T)
+// ================================================================================================
+#define PSM_TILE_N 32
+#define PSM_TILE_K 16
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1},{%2},{%3},{%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <class T, int TM>
+__global__ void __launch_bounds__(256, 2)
+ssssm_tile_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int tiles_per_dest)
+{
+    static_assert(TM % 32 == 0 && TM >= 64 && TM <= 256, "tile height");
+    constexpr int TN = PSM_TILE_N, KC = PSM_TILE_K;
+    constexpr int LDA = TM + 4, LDB = TN + 4;
+    constexpr int WM = TM / 32;          // warps along M
+    constexpr int WN = 8 / WM;           // warps along N
+    constexpr int WTN = TN / WN;         // columns per warp
+    constexpr int NT = WTN / 8;          // 8-column DMMA tiles per warp (double path)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* As0 = sm;                          // [2][KC][LDA]
+    T* Bs0 = sm + 2 * KC * LDA;           // [2][KC][LDB]
+    T* Cs = sm;                           // [TN][LDA], epilogue only
+
+    const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
+    const int d = blockIdx.x / tiles_per_dest;
+    const int c0 = (blockIdx.x % tiles_per_dest) * TN;
+    const SsssmDest<T> D = dests[d];
+    const bool diag = D.u.val != nullptr;
+    const int ncol = min(TN, nb - c0);
+    // nothing to update in these columns?
+    if (!diag && col_begin(D.c.ptr, c0) == D.c.ptr[c0 + ncol]) return;
+
+    // accumulators
+    constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
+    constexpr int NACC = kDouble ? (4 * NT * 2) : (TM / 32) * 4;  // per thread
+    T acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = zero<T>();
+    const int wm = warp % WM, wn = warp / WM;
+    const int m_base = wm * 32, n_base = wn * WTN;
+
+    // zero both tile buffers once
+    for (int i = tid; i < 2 * KC * (LDA + LDB); i += 256) sm[i] = zero<T>();
+    __syncthreads();
+
+    // loader roles
+    const int a_kk = tid / 16, a_l = tid % 16;   // 16 threads per A column
+    const int b_jj = tid / 8, b_l = tid % 8;     // 8 threads per B column
+    const int b_col = c0 + b_jj;
+    const unsigned grp_shift = (lane / 8) * 8;
+
+    int it = 0;
+    for (u32 p = D.pair_begin; p < D.pair_end; ++p)
+    {
+        const BlkRO<T> A = pairs[p].a, B = pairs[p].b;
+        u32 cur = 0, bend = 0;
+        if (b_jj < ncol) { cur = col_begin(B.ptr, b_col); bend = B.ptr[b_col + 1]; }
+        for (int k0 = 0; k0 < nb; k0 += KC)
+        {
+            const int kc = min(KC, nb - k0);
+            const bool a_has = A.ptr[k0 + kc] > col_begin(A.ptr, k0);
+            const int buf = it & 1;
+            T* As = As0 + buf * KC * LDA;
+            T* Bs = Bs0 + buf * KC * LDB;
+            // B piece: rows [k0, k0+kc) of the 32 columns, and advance the per-column cursor
+            {
+                bool in1 = false, in2 = false;
+                u32 e1 = cur + b_l, e2 = cur + 8 + b_l;
+                int r1 = 0, r2 = 0;
+                if (e1 < bend) { r1 = B.idx[e1]; in1 = r1 < k0 + kc; }
+                if (e2 < bend) { r2 = B.idx[e2]; in2 = r2 < k0 + kc; }
+                if (a_has)
+                {
+                    if (in1) Bs[(r1 - k0) * LDB + b_jj] = B.val[e1];
+                    if (in2) Bs[(r2 - k0) * LDB + b_jj] = B.val[e2];
+                }
+                const unsigned m1 = __ballot_sync(PSM_FULL, in1), m2 = __ballot_sync(PSM_FULL, in2);
+                cur += __popc((m1 >> grp_shift) & 0xffu) + __popc((m2 >> grp_shift) & 0xffu);
+            }
+            if (!a_has) continue;  // uniform: nothing to multiply in this chunk
+            // A piece: columns k0 .. k0+kc-1, all rows
+            if (a_kk < kc)
+            {
+                const int k = k0 + a_kk;
+                const u32 a0 = col_begin(A.ptr, k), a1 = A.ptr[k + 1];
+                T* Ak = As + a_kk * LDA;
+                for (u32 e = a0 + a_l; e < a1; e += 16) Ak[A.idx[e]] = A.val[e];
+            }
+            __syncthreads();
+            // clear the other buffer for the next chunk (its last reader finished before the barrier above)
+            {
+                T* Ao = As0 + (buf ^ 1) * KC * LDA;
+                T* Bo = Bs0 + (buf ^ 1) * KC * LDB;
+                for (int i = tid; i < KC * LDA; i += 256) Ao[i] = zero<T>();
+                for (int i = tid; i < KC * LDB; i += 256) Bo[i] = zero<T>();
+            }
+            if constexpr (kDouble)
+            {
+                const int lr = lane / 4, lk = lane % 4;
+#pragma unroll
+                for (int k4 = 0; k4 < KC; k4 += 4)
+                {
+                    double a[4], b[NT];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(k4 + lk) * LDA + m_base + mt * 8 + lr];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) b[nt] = Bs[(k4 + lk) * LDB + n_base + nt * 8 + lr];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) dmma884(acc[(mt * NT + nt) * 2], acc[(mt * NT + nt) * 2 + 1], a[mt], b[nt]);
+                }
+            }
+            else
+            {
+                // FMA register tile: thread (tx, ty) owns rows tx + 32*i (i < TM/32) and columns ty*4 .. ty*4+3
+                const int tx = tid % 32, ty = tid / 32;
+#pragma unroll 4
+                for (int kk = 0; kk < KC; ++kk)
+                {
+                    T bv[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bv[j] = Bs[kk * LDB + ty * 4 + j];
+#pragma unroll
+                    for (int i = 0; i < TM / 32; ++i)
+                    {
+                        const T av = As[kk * LDA + tx + 32 * i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) fma_acc(acc[i * 4 + j], av, bv[j]);
+                    }
+                }
+            }
+            __syncthreads();
+            ++it;
+        }
+    }
+
+    // epilogue: accumulator -> shared memory (column major [TN][LDA]) -> destination pattern
+    __syncthreads();
+    if constexpr (kDouble)
+    {
+        const int lr = lane / 4, lc = (lane % 4) * 2;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+            {
+                const int r = m_base + mt * 8 + lr, c = n_base + nt * 8 + lc;
+                Cs[c * LDA + r] = acc[(mt * NT + nt) * 2];
+                Cs[(c + 1) * LDA + r] = acc[(mt * NT + nt) * 2 + 1];
+            }
+    }
+    else
+    {
+        const int tx = tid % 32, ty = tid / 32;
+#pragma unroll
+        for (int i = 0; i < TM / 32; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Cs[(ty * 4 + j) * LDA + tx + 32 * i] = acc[i * 4 + j];
+    }
+    __syncthreads();
+    for (int jj = warp; jj < ncol; jj += 8)
+    {
+        const int j = c0 + jj;
+        const u32 e0 = col_begin(D.c.ptr, j), e1 = D.c.ptr[j + 1];
+        const T* Cj = Cs + jj * LDA;
+        for (u32 e = e0 + lane; e < e1; e += PSM_WARP) vsub(D.c.val[e], Cj[D.c.idx[e]]);
+    }
+    if (diag)
+    {
+        // upper CSR half: row r holds columns >= r ascending; the tile covers columns [c0, c0+ncol)
+        for (int r = tid; r < min(nb, c0 + ncol); r += 256)
+        {
+            const u32 r0 = col_begin(D.u.ptr, r), r1 = D.u.ptr[r + 1];
+            u32 lo = r0, hi = r1;
+            while (lo < hi)
+            {
+                const u32 mid = (lo + hi) >> 1;
+                if ((int)D.u.idx[mid] < c0) lo = mid + 1;
+                else hi = mid;
+            }
+            for (u32 e = lo; e < r1; ++e)
+            {
+                const int c = D.u.idx[e];
+                if (c >= c0 + ncol) break;
+                vsub(D.u.val[e], Cs[(c - c0) * LDA + r]);
+            }
+        }
+    }
+}
+
 }  // namespace psm

@@ -105,6 +105,24 @@ def test_gstrf_other_types(vtype):
         s.finalize()
 
 
+@pytest.mark.parametrize("ssssm_mode", [1, 2], ids=["all-sparse", "all-tile"])
+def test_gstrf_forced_ssssm_path(ssssm_mode):
+    """The two SSSSM kernels must be interchangeable: force every update through one of them."""
+    A = matrices.poisson3d(12)
+    nb = 64
+    want, _, _ = _expected(A, nb, "r64")
+    L = _lib.load("r64")
+    L.pangulu_sm100_set_option(b"ssssm_mode", ssssm_mode)
+    s = PanguLU(A, nb=nb, mode=0)
+    try:
+        s.gstrf()
+        worst = max(rel_err(g.value, w.value) for g, w in zip(s.blocks(copy=True), want))
+        assert worst <= TOL["r64"]
+    finally:
+        L.pangulu_sm100_set_option(b"ssssm_mode", 0)
+        s.finalize()
+
+
 def test_refactor_after_reset():
     """gstrf twice on one handle (values reset in between) gives the same factors: idempotence of the
     reset + factor cycle used by bench.py."""

@@ -55,10 +55,19 @@ def _index(blocks):
     return off, diag
 
 
+@pytest.fixture(params=[1, 2], ids=["ssssm-sparse", "ssssm-tile"])
+def ssssm_mode(request):
+    """Force the SSSSM path: 1 = sparse scatter kernel, 2 = dense-tile (DMMA / FMA tile) kernel."""
+    yield request.param
+    for vt in ("r64", "r32", "cr64", "cr32"):
+        _lib.load(vt).pangulu_sm100_set_option(b"ssssm_mode", 0)
+
+
 @pytest.mark.parametrize("vtype", ["r64", "r32", "cr64", "cr32"])
 @pytest.mark.parametrize("name,make,nb", CASES, ids=[c[0] for c in CASES])
-def test_single_kernels(name, make, nb, vtype):
+def test_single_kernels(name, make, nb, vtype, ssssm_mode):
     dtype = _lib.VALUE_DTYPES[vtype]
+    _lib.load(vtype).pangulu_sm100_set_option(b"ssssm_mode", ssssm_mode)
     blocks = blocks_of(make(), nb, vtype)
     rng = np.random.default_rng(1234)
     _randomise(blocks, rng, dtype)
@@ -132,11 +141,12 @@ def test_single_kernels(name, make, nb, vtype):
 
 
 @pytest.mark.parametrize("vtype", ["r64", "r32"])
-def test_hybrid_batched_same_destination(vtype):
+def test_hybrid_batched_same_destination(vtype, ssssm_mode):
     """Several SSSSM tasks with the SAME opdst in one hybrid_batched call (the aggregator's batches,
     src/pangulu_task.c:39-91) must be combined, not raced."""
     nb = 32
     dtype = _lib.VALUE_DTYPES[vtype]
+    _lib.load(vtype).pangulu_sm100_set_option(b"ssssm_mode", ssssm_mode)
     blocks = blocks_of(matrices.poisson3d(8), nb, vtype)
     rng = np.random.default_rng(7)
     _randomise(blocks, rng, dtype)
@@ -153,7 +163,17 @@ def test_hybrid_batched_same_destination(vtype):
                 for j in cols:
                     if i == j or (i, j) in off:
                         upd.setdefault((i, j), []).append(k)
-        dests = sorted(upd, key=lambda d: -len(upd[d]))[:6]
+        # a batch never reads a block it also updates (operands are finished blocks): keep destinations
+        # whose operands are not destinations of the batch and vice versa
+        dests, used_as_operand = [], set()
+        for d in sorted(upd, key=lambda d: -len(upd[d])):
+            ops = {(d[0], k) for k in upd[d]} | {(k, d[1]) for k in upd[d]}
+            if d in used_as_operand or ops & set(dests):
+                continue
+            dests.append(d)
+            used_as_operand |= ops
+            if len(dests) == 6:
+                break
         assert len(upd[dests[0]]) >= 2
         tasks = []
         slots = {}
