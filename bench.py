@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- gstrf GFLOP/s and wall time of PanguLU's numeric factorisation on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--size S] [--nb NB]
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on; it fits one GPU): synthetic 3D 7-point
+Poisson matrix on a 100^3 grid (1 000 000 rows), R64, METIS_NodeND ordering, nb = 256.  One "step" is one
+pangulu_gstrf over the whole matrix.  GFLOP/s uses the reference's own flop model
+(src/pangulu_kernel_interface.c:4-176), which depends on the structure only.
+
+Our arm prints one JSON line with
+  value      : GFLOP/s with the blocks already resident in HBM (device-resident static plan), timed with CUDA
+               events on the module's stream, max over ranks
+  e2e        : the same metric through the reference-facing C ABI call path: factor values start in HOST
+               block buffers, are uploaded, every wave goes through pangulu_platform_0201001_hybrid_batched
+               with a HOST task array, finished factors are downloaded -- all inside the timed region
+  roofline   : dominant kernel class (by device time), algorithmic bytes or flops / device time
+  cpu_baseline : the unmodified reference CPU platform (oracle/_ref) on a bounded sample of the same workload
+`--impl reference` times the reference's own CPU implementation (oracle/_ref) instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "gstrf_gflops"
+UNIT = "GFLOP/s"
+NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 / FP64-tensor nominal peak (no measured FP64 number in MEASURED_PEAKS.json)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--size", type=int, default=100, help="grid points per dimension (default: the named config, 100)")
+    ap.add_argument("--nb", type=int, default=256)
+    ap.add_argument("--ref-size", type=int, default=32, help="grid size of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(size, nb):
+    return f"poisson3d_7pt_{size}^3_r64_metis_nb{nb}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smmax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the unmodified reference CPU platform on a bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def reference_step(size, nb):
+    """One reference pangulu_gstrf (fresh process; the reference is single-shot). Returns (gflops, seconds, flop, blas)."""
+    from oracle.ref_run import run_reference
+    from pangulu_b200 import matrices
+
+    A = matrices.poisson3d(size)
+    z = run_reference(A, nb, vtype="r64", perf=False, solve=False, blocks=False, nthread=1)
+    return float(z["t_gstrf"]), str(z["blas"])
+
+
+def sample_flop(size, nb):
+    """Reference-model flop count of the sample (structure only) from our host-only structure pass."""
+    from pangulu_b200 import PanguLU, matrices
+
+    s = PanguLU(matrices.poisson3d(size), nb=nb, host_only=True)
+    f = s.info("flop")
+    s.finalize()
+    return f
+
+
+def cpu_baseline(size, nb, reps=1):
+    from oracle.ref import ref_available
+
+    if not ref_available("r64"):
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref missing on this box"}
+    flop = sample_flop(size, nb)
+    best, blas = None, ""
+    for _ in range(reps):
+        t, blas = reference_step(size, nb)
+        best = t if best is None else min(best, t)
+    return {"value": flop / best / 1e9, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": best,
+            "sample": f"unmodified reference CPU platform 0100000 (1 rank: the image has no MPI; 1 compute thread as the reference "
+                      f"runs its kernels with tid 0; BLAS {blas.split('/')[-1] or 'builtin'}) on poisson3d {size}^3 nb={nb}, "
+                      f"{flop:.3e} flop"}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    size, nb = a.ref_size, a.nb
+    flop = sample_flop(size, nb)
+    times = []
+    blas = ""
+    for i in range(a.warmup + a.steps):
+        t, blas = reference_step(size, nb)
+        if i >= a.warmup:
+            times.append(t)
+    t = sum(times) / len(times)
+    v = flop / t / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(a.size, a.nb), "sample": f"poisson3d {size}^3 nb={nb} (bounded CPU sample)"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "reference",
+                             "sample": f"reference CPU platform, 1 rank x 1 compute thread, BLAS {blas.split('/')[-1] or 'builtin'}, poisson3d {size}^3 nb={nb}"},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------------
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+
+    from pangulu_b200 import PanguLU, matrices
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the numeric factorisation has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        raise SystemExit("multi-GPU gstrf is not wired into bench.py yet")
+
+    A = matrices.poisson3d(a.size)
+    n = A.shape[0]
+    t0 = time.time()
+    s = PanguLU(A, nb=a.nb, mode=1, rank=rank, nproc=world)
+    t_init = time.time() - t0
+    L = s.L
+    flop = s.info("flop")
+    stream = torch.cuda.ExternalStream(L.pangulu_sm100_stream())
+
+    # ---- resident (value): device-resident plan, CUDA events on the module's stream -----------------
+    s.set_mode(1)
+    times = []
+    sampler = ClockSampler(local_rank)
+    class_ms = None
+    launches = 0
+    for it in range(a.warmup + a.steps):
+        if it > 0:
+            s.reset_values(True)           # untimed: fresh values of A in the HBM block buffers
+        timed = it >= a.warmup
+        if it == a.warmup:
+            sampler.start()
+            L.pangulu_sm100_stats_reset()
+            L.pangulu_sm100_set_option(b"profile", 1)   # async event pairs around every launch, no host sync
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        s.gstrf_enqueue()
+        e1.record(stream)
+        e1.synchronize()
+        torch.cuda.synchronize()
+        if timed:
+            times.append(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    class_ms = [L.pangulu_sm100_stats_ms(c) / a.steps for c in range(6)]
+    class_launches = [L.pangulu_sm100_stats_launches(c) / a.steps for c in range(6)]
+    launches = int(sum(class_launches[:5]))
+    L.pangulu_sm100_set_option(b"profile", 0)
+    ms = sum(times) / len(times)
+    value = flop / (ms * 1e-3) / 1e9
+
+    # parity spot-check of what was just timed (size-independent property: ||L(U1) - A1|| / ||A1||)
+    s.download()
+    check = s.factor_check()
+
+    # ---- e2e: reference-facing call path with host buffers --------------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        s.set_mode(0)
+        et = []
+        for it in range(1 + max(1, a.steps)):
+            s.reset_values(False)          # host block buffers <- A (untimed)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.gstrf()                      # H2D values + per-wave hybrid_batched(host tasks) + D2H factors
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if it >= 1:
+                et.append(dt)
+        e2e_t = sum(et) / len(et)
+        e2e = {"value": flop / e2e_t / 1e9, "unit": UNIT, "seconds": e2e_t,
+               "h2d_bytes_per_step": int(s.info("value_bytes")) + int(s.info("ntask")) * 48,
+               "d2h_bytes_per_step": int(s.info("own_value_bytes"))}
+        check_e2e = s.factor_check()
+    else:
+        check_e2e = None
+
+    # ---- roofline of the dominant kernel class -------------------------------------------------------------
+    peaks, peak_kind = measured_peaks()
+    names = ["getrf", "tstrf+gessm", "-", "ssssm_sparse", "ssssm_tile", "aux"]
+    dom = max(range(5), key=lambda c: class_ms[c])
+    ssssm_ms = class_ms[3] + class_ms[4]
+    roof = {}
+    if dom in (3, 4):
+        # SSSSM: algorithmic bytes of all SSSSM tasks over the device time of both SSSSM kernels
+        by = s.info("bytes_ssssm")
+        ach = by / (ssssm_ms * 1e-3) / 1e9
+        roof = {"kernel": "ssssm (sparse + tile kernels)", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": f"hbm copy bandwidth, {peak_kind}",
+                "launches_per_step": class_launches[3] + class_launches[4], "ms_per_step": ssssm_ms,
+                "flops_tflops": s.info("flop_ssssm") / (ssssm_ms * 1e-3) / 1e12,
+                "fp64_frac_of_nominal": s.info("flop_ssssm") / (ssssm_ms * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS}
+    else:
+        key = "bytes_getrf" if dom == 0 else None
+        by = s.info("bytes_getrf") if dom == 0 else s.info("bytes_tstrf") + s.info("bytes_gessm")
+        ach = by / (class_ms[dom] * 1e-3) / 1e9
+        roof = {"kernel": names[dom], "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": f"hbm copy bandwidth, {peak_kind}",
+                "launches_per_step": class_launches[dom], "ms_per_step": class_ms[dom]}
+    roof["class_ms"] = {names[c]: class_ms[c] for c in range(5) if c != 2}
+
+    cpu = None
+    if not a.no_cpu_baseline:
+        cpu = cpu_baseline(a.ref_size, a.nb)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": workload_name(a.size, a.nb), "n": n, "nnz_A": int(A.nnz), "nnz_LU": int(s.info("symbolic_nnz")),
+                       "flop_per_step": flop, "nb": a.nb, "ordering": "METIS_NodeND (CUDA toolkit libmetis_static.a)",
+                       "waves": int(s.info("nwave")), "tasks": int(s.info("ntask")),
+                       "l2": "inputs (factor values %.1f GB) exceed the 126 MB L2; values are rewritten between steps" % (s.info("value_bytes") / 1e9),
+                       "init_seconds": t_init},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "parity": {"factor_check_resident": check, "factor_check_e2e": check_e2e}}
+    s.finalize()
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

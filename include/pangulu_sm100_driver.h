@@ -69,6 +69,9 @@ const void *pangulu_sm100_driver_perm(void *handle, int which);
 const pangulu_task_t *pangulu_sm100_driver_tasks(void *handle, const pangulu_uint64_t **wave_ptr);
 /* put the values of A back into the host block buffers (and the device copy) so gstrf can run again */
 void pangulu_sm100_driver_reset_values(void *handle, int also_device);
+/* resident mode: enqueue the whole factorisation on the module's stream (pangulu_sm100_stream()) without
+ * synchronising; <id>_synchronize() or a stream event completes it */
+void pangulu_sm100_driver_gstrf_enqueue(void *handle);
 /* device -> host copy of the owned factors (resident mode) */
 void pangulu_sm100_driver_download(void *handle);
 /* the reference's gstrf self-check ||L(U1) - A1|| / ||A1|| (src/pangulu_numeric.c:1082-1341) on host factors */

@@ -113,7 +113,12 @@ def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthre
             cmd.append("--no-solve")
         if not blocks:
             cmd.append("--no-blocks")
-        r = subprocess.run(cmd, cwd=_ROOT, stdout=subprocess.PIPE if quiet else None, stderr=subprocess.STDOUT if quiet else None)
+        # The reference leaves the value arrays of some fill-in entries uninitialised (malloc without memset in its
+        # block construction); on small problems recycled heap memory then shows up as garbage, even NaN, in the
+        # factors.  glibc's MALLOC_PERTURB_=255 makes malloc hand out zero-filled memory (byte ^ 0xff), which is what
+        # the algorithm assumes -- the reference sources stay untouched.
+        env = dict(os.environ, MALLOC_PERTURB_="255")
+        r = subprocess.run(cmd, cwd=_ROOT, env=env, stdout=subprocess.PIPE if quiet else None, stderr=subprocess.STDOUT if quiet else None)
         if r.returncode != 0:
             raise RuntimeError("reference run failed:\n" + (r.stdout.decode(errors="replace") if r.stdout else ""))
         with np.load(out, allow_pickle=False) as z:

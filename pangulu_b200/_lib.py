@@ -36,7 +36,7 @@ DRIVER_FUNCTIONS = [
     "pangulu_init", "pangulu_gstrf", "pangulu_gstrs", "pangulu_gssv", "pangulu_finalize",
     "pangulu_sm100_driver_config", "pangulu_sm100_driver_info", "pangulu_sm100_driver_slot",
     "pangulu_sm100_driver_perm", "pangulu_sm100_driver_tasks", "pangulu_sm100_driver_reset_values",
-    "pangulu_sm100_driver_download", "pangulu_sm100_driver_factor_check",
+    "pangulu_sm100_driver_download", "pangulu_sm100_driver_factor_check", "pangulu_sm100_driver_gstrf_enqueue",
 ]
 
 
@@ -151,6 +151,7 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_driver_tasks.restype = vp
     L.pangulu_sm100_driver_reset_values.argtypes = [vp, C.c_int]
     L.pangulu_sm100_driver_download.argtypes = [vp]
+    L.pangulu_sm100_driver_gstrf_enqueue.argtypes = [vp]
     L.pangulu_sm100_driver_factor_check.argtypes = [vp]
     L.pangulu_sm100_driver_factor_check.restype = C.c_double
     L.platform = P

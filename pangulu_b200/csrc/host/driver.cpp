@@ -176,6 +176,14 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         fprintf(stderr, "[PanguLU ERROR] handle was created in host_only (structure) mode; numeric factorisation needs the GPU -- there is no CPU path\n");
         exit(EXIT_FAILURE);
     }
+    h->mode = (int)g_cfg.mode;  // the mode may be switched between calls (bench.py times both on one handle)
+    if (h->mode == 1 && !h->plan)
+    {
+        const double tp = wall_seconds();
+        h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
+                                            h->sched.tasks.data());
+        h->times["plan"] = wall_seconds() - tp;
+    }
     const double t0 = wall_seconds();
     if (h->mode == 1 && g_cfg.nproc == 1)
     {
@@ -321,6 +329,23 @@ void pangulu_sm100_driver_reset_values(void* handle, int also_device)
     scatter_values(h);
     if (also_device && !h->B.host_only) PSM(memcpy)(h->B.d_buf, h->B.h_buf, h->B.value_bytes, 0);
     h->factored = false;
+}
+
+// resident mode only: enqueue the whole factorisation on the module's stream and return without
+// synchronising (bench.py brackets it with CUDA events on that stream)
+void pangulu_sm100_driver_gstrf_enqueue(void* handle)
+{
+    Handle* h = (Handle*)handle;
+    if (h->B.host_only)
+    {
+        fprintf(stderr, "[PanguLU ERROR] host_only handle: numeric factorisation needs the GPU -- there is no CPU path\n");
+        exit(EXIT_FAILURE);
+    }
+    if (!h->plan)
+        h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
+                                            h->sched.tasks.data());
+    pangulu_sm100_plan_execute(h->plan);
+    h->factored = true;
 }
 
 void pangulu_sm100_driver_download(void* handle)

@@ -105,6 +105,16 @@ class PanguLU:
     def reset_values(self, also_device: bool = True) -> None:
         self.L.pangulu_sm100_driver_reset_values(self._h, int(also_device))
 
+    def gstrf_enqueue(self) -> None:
+        """Resident mode: enqueue the factorisation on the module's stream without synchronising."""
+        self.L.pangulu_sm100_driver_gstrf_enqueue(self._h)
+
+    def synchronize(self) -> None:
+        self.L.platform("synchronize")()
+
+    def set_mode(self, mode: int) -> None:
+        driver_config(self.vtype, mode=mode)
+
     def download(self) -> None:
         self.L.pangulu_sm100_driver_download(self._h)
 

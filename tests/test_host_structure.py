@@ -1,0 +1,133 @@
+"""Host logic of the driver (no GPU): reordering, symbolic pattern, block storage, schedule and flop model,
+checked bit for bit against the golden vectors from the unmodified reference and against live reference runs."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from helpers import GOLDEN
+from oracle.ref_run import unflatten
+from pangulu_b200 import PanguLU, _lib, matrices
+
+GOLDEN_CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")) if "pattern" not in p)
+
+
+def _same_structure(mine, ref_blocks):
+    assert len(mine) == len(ref_blocks)
+    for a, b in zip(mine, ref_blocks):
+        assert (a.brow, a.bcol, a.is_upper) == (b.brow, b.bcol, b.is_upper)
+        assert np.array_equal(a.colptr, b.colptr) and np.array_equal(a.rowidx, b.rowidx)
+        assert np.array_equal(a.value, b.value)  # A's values scattered into the zero-filled pattern
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_structure_perm_and_flops_match_golden(case):
+    z = np.load(os.path.join(GOLDEN, case + ".npz"))
+    n, nb = int(z["n"]), int(z["nb"])
+    A = sp.csc_matrix((z["A_data"], z["A_indices"], z["A_indptr"]), shape=(n, n))
+    s = PanguLU(A, nb=nb, host_only=True)
+    try:
+        assert int(s.info("symbolic_nnz")) == int(z["symbolic_nnz"])
+        assert np.array_equal(s.perms()["metis_perm"], z["metis_perm"])  # permutation indices: bit-exact
+        _same_structure(s.blocks(), unflatten(z, "pre_", nb))
+        assert int(s.info("flop")) == int(z["flop"])  # closed-form flop model == reference's merge-based counter
+    finally:
+        s.finalize()
+
+
+@pytest.mark.parametrize("make,nb", [(lambda: matrices.poisson3d(14), 64), (lambda: matrices.laplace2d(60), 48),
+                                     (lambda: matrices.stencil27(9), 128), (lambda: matrices.circuit_like(800, dmax=30, dtype=np.float64), 40)],
+                         ids=["poisson3d-14", "laplace2d-60", "stencil27-9", "circuit-800"])
+def test_structure_matches_live_reference(make, nb):
+    from oracle.ref import ref_available
+    from oracle.ref_run import run_reference
+
+    if not ref_available("r64"):
+        pytest.skip("oracle/_ref not built on this box")
+    A = make()
+    z = run_reference(A, nb, perf=True, solve=False)
+    s = PanguLU(A, nb=nb, host_only=True)
+    try:
+        assert np.array_equal(s.perms()["metis_perm"], z["metis_perm"])
+        _same_structure(s.blocks(), unflatten(z, "pre_", nb))
+        assert int(s.info("flop")) == int(z["flop"])
+        # CSR mirrors of strictly-lower blocks equal the reference routine's output
+        from oracle.ref_run import add_csr_mirror
+
+        for b in s.blocks():
+            if b.brow > b.bcol:
+                from types import SimpleNamespace
+
+                m = add_csr_mirror(SimpleNamespace(colptr=b.colptr, rowidx=b.rowidx), nb)
+                assert np.array_equal(m.rowptr, b.rowptr) and np.array_equal(m.colidx, b.colidx) and np.array_equal(m.csr2csc, b.csr2csc)
+    finally:
+        s.finalize()
+
+
+def test_schedule_respects_dependencies():
+    """Every task of the static schedule runs in a later wave than the tasks that produce its operands, and all
+    updates of a destination sit in the wave that finalises it."""
+    A = matrices.poisson3d(12)
+    nb = 32
+    s = PanguLU(A, nb=nb, host_only=True)
+    try:
+        tasks, wave_ptr = s.schedule()
+        wave_of_task = np.repeat(np.arange(len(wave_ptr) - 1), np.diff(wave_ptr.astype(np.int64)))
+        final = {}  # slot address -> wave in which the block is finalised (diag: keyed by the lower half)
+        slot_addr = {}
+        for i in range(int(s.info("num_slots"))):
+            p = s.slot_ptr(i)
+            sl = p.contents
+            slot_addr[(sl.brow_pos, sl.bcol_pos, sl.is_upper)] = C_addr(p)
+        for t, w in zip(tasks, wave_of_task):
+            if t["kernel_id"] != _lib.TASK_SSSSM:
+                final[int(t["opdst"])] = w
+        n_upd = 0
+        for t, w in zip(tasks, wave_of_task):
+            k = int(t["task_level"])
+            diag_lower = slot_addr[(k, k, 0)]
+            if t["kernel_id"] in (_lib.TASK_TSTRF, _lib.TASK_GESSM):
+                assert final[diag_lower] < w
+            if t["kernel_id"] == _lib.TASK_SSSSM:
+                assert final[int(t["op1"])] < w and final[int(t["op2"])] < w
+                assert final[int(t["opdst"])] == w  # applied in the wave that finalises the destination
+                n_upd += 1
+        assert n_upd == int(s.info("n_ssssm")) and n_upd > 0
+        # within a wave: SSSSM first, then GETRF, then TSTRF/GESSM
+        for w in range(len(wave_ptr) - 1):
+            ids = tasks["kernel_id"][int(wave_ptr[w]):int(wave_ptr[w + 1])]
+            cls = np.where(ids == _lib.TASK_SSSSM, 0, np.where(ids == _lib.TASK_GETRF, 1, 2))
+            assert np.all(np.diff(cls) >= 0)
+    finally:
+        s.finalize()
+
+
+def C_addr(ptr):
+    import ctypes
+
+    return ctypes.addressof(ptr.contents)
+
+
+@pytest.mark.parametrize("nproc", [2, 4, 8])
+def test_block_cyclic_ownership_partitions_the_tasks(nproc):
+    """2D block-cyclic owner-computes (src/pangulu_common.h:135, src/pangulu.c:83-90): the ranks' task lists are a
+    partition of the single-rank list, and every operand a rank reads is a block it holds."""
+    A = matrices.poisson3d(10)
+    nb = 32
+    base = PanguLU(A, nb=nb, host_only=True)
+    t0, _ = base.schedule()
+    all_tasks = sorted((int(t["row"]), int(t["col"]), int(t["kernel_id"]), int(t["task_level"])) for t in t0)
+    base.finalize()
+    got = []
+    pq = {2: (1, 2), 4: (2, 2), 8: (2, 4)}[nproc]
+    for r in range(nproc):
+        s = PanguLU(A, nb=nb, host_only=True, rank=r, nproc=nproc)
+        assert (int(s.info("p")), int(s.info("q"))) == pq
+        t, _ = s.schedule()
+        for x in t:
+            assert (int(x["row"]) % pq[0]) * pq[1] + int(x["col"]) % pq[1] == r
+        got += [(int(x["row"]), int(x["col"]), int(x["kernel_id"]), int(x["task_level"])) for x in t]
+        s.finalize()
+    assert sorted(got) == all_tasks
