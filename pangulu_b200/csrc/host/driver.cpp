@@ -34,6 +34,7 @@ struct DriverConfig
     long long mode = 0;
     long long verbose = 0;
     long long host_only = 0;
+    long long schedule = 1;
 };
 DriverConfig g_cfg;
 
@@ -68,6 +69,7 @@ int pangulu_sm100_driver_config(const char* key, long long value)
     else if (k == "mode") g_cfg.mode = value;
     else if (k == "verbose") g_cfg.verbose = value;
     else if (k == "host_only") g_cfg.host_only = value;
+    else if (k == "schedule") g_cfg.schedule = value;
     else return -1;
     return 0;
 }
@@ -147,6 +149,7 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     // the element-level pattern is not needed after blocking
     std::vector<eidx>().swap(h->S.idx);
     t0 = wall_seconds();
+    h->sched.policy = (int)g_cfg.schedule;
     build_schedule(h->B, h->sched);
     h->times["schedule"] = wall_seconds() - t0;
     t0 = wall_seconds();

@@ -101,7 +101,7 @@ void build_schedule(BlockStore& B, Schedule& S)
                     maxdep_diag[i] = std::max(maxdep_diag[i], m);
                     if (B.owner(i, i) == B.rank)
                     {
-                        Proto t{0, 0, PANGULU_TASK_SSSSM, i, i, k, B.slot_of_diag[i], slot_off(gid_l[a]), slot_off(gid_u[b])};
+                        Proto t{m + 1, 0, PANGULU_TASK_SSSSM, i, i, k, B.slot_of_diag[i], slot_off(gid_l[a]), slot_off(gid_u[b])};
                         protos.push_back(t);
                         S.n_ssssm++;
                     }
@@ -113,7 +113,7 @@ void build_schedule(BlockStore& B, Schedule& S)
                     maxdep_off[g] = std::max(maxdep_off[g], m);
                     if (B.owner(i, j) == B.rank)
                     {
-                        Proto t{0, 0, PANGULU_TASK_SSSSM, i, j, k, slot_off((int64_t)g), slot_off(gid_l[a]), slot_off(gid_u[b])};
+                        Proto t{m + 1, 0, PANGULU_TASK_SSSSM, i, j, k, slot_off((int64_t)g), slot_off(gid_l[a]), slot_off(gid_u[b])};
                         protos.push_back(t);
                         S.n_ssssm++;
                     }
@@ -121,11 +121,15 @@ void build_schedule(BlockStore& B, Schedule& S)
             }
         }
     }
-    // wave of an update = depth of its destination (known only after all levels were seen)
+    // wave of an update:
+    //   policy 0 (lazy, left-looking)  = depth of its destination (known only after all levels were seen): a
+    //            destination is read and written once, but its updates pile up on the critical path;
+    //   policy 1 (eager, right-looking) = 1 + max(depth of its operands), already stored: the update runs as soon
+    //            as both panel blocks are final -- wide waves, and only the last update precedes the panel op.
     int32_t nwave = 0;
     for (auto& t : protos)
     {
-        if (t.cls == 0)
+        if (t.cls == 0 && S.policy == 0)
         {
             if (t.row == t.col) t.wave = S.depth_diag[t.row];
             else t.wave = S.depth_offdiag[B.find_block(t.row, t.col)];

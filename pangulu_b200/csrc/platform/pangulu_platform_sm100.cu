@@ -46,6 +46,7 @@ typedef calculate_type T;
 #define CK_LAST() CK(cudaGetLastError())
 
 enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_NCLASS = 6 };
+enum { K_GETRF_SMEM = 100, K_GETRF_DENSE = 101 };  // step kinds only; accounted under K_GETRF
 
 struct Options
 {
@@ -53,6 +54,9 @@ struct Options
     long long dense_threshold = 250;
     long long ssssm_mode = 0;
     long long profile = 0;
+    long long getrf_mode = 0;  // 0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense
+    long long tile_variant = 2; // 2 pipelined 512-thread tile kernel, 1 first-generation 256-thread kernel
+    long long split_pairs = 1;  // split heavy destinations of thin waves over several CTAs
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -171,12 +175,18 @@ inline void diag_halves(pangulu_storage_slot_t* s, pangulu_storage_slot_t*& lowe
     if (!lower || !upper) fatal(__FILE__, __LINE__, "diagonal block without its related half", nullptr);
 }
 
+inline size_t getrf_smem_bytes(int nb, size_t nl, size_t nu)
+{
+    return ((size_t)(4 * nb + nl + nu) * sizeof(T) + 8 * (size_t)(nb + 1) + 2 * (nl + nu) + 15) & ~(size_t)15;
+}
+
 // ---- batch program: what one hybrid_batched call / one plan wave turns into --------------------------
 struct Step
 {
     int kind;          // KClass of the launch, or -1 for a device->host value download
     size_t off;        // first descriptor (index into the class's array)
     size_t count;      // descriptors (GETRF tasks / panel tasks / SSSSM destinations)
+    size_t smem = 0;   // dynamic shared memory of the launch where it depends on the batch
 };
 struct Download { void* h; const void* d; size_t bytes; };
 
@@ -274,6 +284,34 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 P.pairs.push_back(pr);
                 by_cls[cur_cls].back().pair_end = (u32)P.pairs.size();
             }
+            // Few, heavy destinations (the fronts of the top separators) would leave most SMs idle: split their
+            // operand-pair ranges over several CTAs, which then combine with global FP64 reductions (flags bit 0).
+            if (!by_cls[0].empty() && g.opt.split_pairs != 0)
+            {
+                const size_t tiles = (size_t)(nb + PSM_TILE_N - 1) / PSM_TILE_N;
+                const size_t target = 2 * (size_t)g.sm_count;
+                size_t total_pairs = 0;
+                for (auto& D0 : by_cls[0]) total_pairs += D0.pair_end - D0.pair_begin;
+                if (by_cls[0].size() * tiles < target && total_pairs > by_cls[0].size())
+                {
+                    const size_t per = std::max<size_t>(1, (total_pairs * tiles + target - 1) / target);
+                    std::vector<SsssmDest<T>> split;
+                    for (auto& D0 : by_cls[0])
+                    {
+                        const u32 np = D0.pair_end - D0.pair_begin;
+                        if (np <= per) { split.push_back(D0); continue; }
+                        for (u32 b0 = D0.pair_begin; b0 < D0.pair_end; b0 += (u32)per)
+                        {
+                            SsssmDest<T> piece = D0;
+                            piece.pair_begin = b0;
+                            piece.pair_end = std::min<u32>(D0.pair_end, b0 + (u32)per);
+                            piece.flags |= 1u;
+                            split.push_back(piece);
+                        }
+                    }
+                    by_cls[0].swap(split);
+                }
+            }
             for (int c = 0; c < 2; ++c)
             {
                 if (by_cls[c].empty()) continue;
@@ -293,7 +331,9 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
         else if (kid == PANGULU_TASK_GETRF)
         {
             size_t j = i;
-            Step st; st.kind = K_GETRF; st.off = P.getrf.size(); st.count = 0;
+            // diagonal blocks that fit in shared memory (values + pattern of both halves) take the staged kernel
+            std::vector<GetrfTask<T>> fit, big;
+            size_t fit_smem = 0;
             Step dl; dl.kind = -1; dl.off = P.downloads.size(); dl.count = 0;
             while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_GETRF)
             {
@@ -302,17 +342,33 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 GetrfTask<T> G;
                 G.lower = blk_csc(lo);
                 G.upper = blk_upper_diag(up);
-                P.getrf.push_back(G);
-                st.count++;
+                const size_t nl = slot_nnz(nb, lo), nu = slot_nnz(nb, up);
+                const size_t need = getrf_smem_bytes(nb, nl, nu);
+                // getrf_mode: 0 auto, 1 never stage in shared memory, 2 never promote to dense, 3 always dense (nb <= 256)
+                const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256;
+                if (!want_dense && need <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); }
+                else big.push_back(G);
                 if (eager_download)
                 {
-                    P.downloads.push_back({lo->value, lo->d_value, sizeof(T) * (size_t)slot_nnz(nb, lo)});
-                    P.downloads.push_back({up->value, up->d_value, sizeof(T) * (size_t)slot_nnz(nb, up)});
+                    P.downloads.push_back({lo->value, lo->d_value, sizeof(T) * nl});
+                    P.downloads.push_back({up->value, up->d_value, sizeof(T) * nu});
                     dl.count += 2;
                 }
                 ++j;
             }
-            P.steps.push_back(st);
+            if (!fit.empty())
+            {
+                Step st; st.kind = K_GETRF_SMEM; st.off = P.getrf.size(); st.count = fit.size(); st.smem = fit_smem;
+                P.getrf.insert(P.getrf.end(), fit.begin(), fit.end());
+                P.steps.push_back(st);
+            }
+            if (!big.empty())
+            {
+                // too full for shared memory: dense-promoted blocked LU (nb <= 256), else the global-memory sparse kernel
+                Step st; st.kind = (nb <= 256 && g.opt.getrf_mode != 2) ? (int)K_GETRF_DENSE : (int)K_GETRF; st.off = P.getrf.size(); st.count = big.size(); st.smem = 0;
+                P.getrf.insert(P.getrf.end(), big.begin(), big.end());
+                P.steps.push_back(st);
+            }
             if (dl.count) P.steps.push_back(dl);
             i = j;
         }
@@ -440,10 +496,26 @@ template <int TM> void launch_ssssm_tile_t(int nb, const SsssmDest<T>* d, const 
     ssssm_tile_kernel<T, TM><<<(unsigned)(ndest * tiles), 256, smem, g.stream>>>(nb, d, p, tiles);
     CK_LAST();
 }
+template <int TM> void launch_ssssm_tile2_t(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
+{
+    const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
+    const size_t a = (size_t)2 * PSM_TILE_K * (TM + 4 + PSM_TILE_N + 4), c = (size_t)PSM_TILE_N * (TM + 4);
+    const size_t smem = std::max(a, c) * sizeof(T);
+    set_smem(ssssm_tile2_kernel<T, TM>, smem);
+    ssssm_tile2_kernel<T, TM><<<(unsigned)(ndest * tiles), 512, smem, g.stream>>>(nb, d, p, tiles);
+    CK_LAST();
+}
 void launch_ssssm_tile(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, size_t ndest)
 {
     if (!ndest) return;
     Timer tm(K_SSSSM_TILE);
+    if (g.opt.tile_variant != 1)
+    {
+        if (nb <= 128) launch_ssssm_tile2_t<128>(nb, d, p, ndest);
+        else launch_ssssm_tile2_t<256>(nb, d, p, ndest);
+        g.launches[K_SSSSM_TILE]++;
+        return;
+    }
     if (nb <= 64) launch_ssssm_tile_t<64>(nb, d, p, ndest);
     else if (nb <= 128) launch_ssssm_tile_t<128>(nb, d, p, ndest);
     else launch_ssssm_tile_t<256>(nb, d, p, ndest);
@@ -480,6 +552,42 @@ void launch_getrf(int nb, const GetrfTask<T>* t, size_t n)
     CK_LAST();
     g.launches[K_GETRF]++;
 }
+// L2-resident scratch of the dense-promoted GETRF (grow-only; growing waits for the stream to drain)
+T* g_scratch = nullptr;
+size_t g_scratch_bytes = 0;
+T* ensure_scratch(size_t bytes)
+{
+    if (bytes > g_scratch_bytes)
+    {
+        CK(cudaStreamSynchronize(g.stream));
+        if (g_scratch) CK(cudaFree(g_scratch));
+        g_scratch_bytes = std::max(bytes, (size_t)8 << 20);
+        CK(cudaMalloc((void**)&g_scratch, g_scratch_bytes));
+    }
+    return g_scratch;
+}
+void launch_getrf_dense(int nb, const GetrfTask<T>* t, size_t n)
+{
+    if (!n) return;
+    const int nbp = (nb + 31) & ~31;
+    T* scratch = ensure_scratch(n * (size_t)nbp * nbp * sizeof(T));
+    Timer tm(K_GETRF);
+    const size_t smem = ((size_t)2 * PSM_GETRF_W * nbp + 64) * sizeof(T);
+    set_smem(getrf_dense_kernel<T>, smem);
+    getrf_dense_kernel<T><<<(unsigned)n, 256, smem, g.stream>>>(nb, t, scratch);
+    CK_LAST();
+    g.launches[K_GETRF]++;
+}
+void launch_getrf_smem(int nb, const GetrfTask<T>* t, size_t n, size_t smem)
+{
+    if (!n) return;
+    Timer tm(K_GETRF);
+    constexpr int THREADS = 256;
+    set_smem(getrf_smem_kernel<T, THREADS>, smem);
+    getrf_smem_kernel<T, THREADS><<<(unsigned)n, THREADS, smem, g.stream>>>(nb, t);
+    CK_LAST();
+    g.launches[K_GETRF]++;
+}
 
 void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t s1)
 {
@@ -491,6 +599,8 @@ void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t 
         case K_SSSSM_SPARSE: launch_ssssm_sparse(nb, D.dests + st.off, D.pairs, st.count); break;
         case K_SSSSM_TILE: launch_ssssm_tile(nb, D.dests + st.off, D.pairs, st.count); break;
         case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); break;
+        case K_GETRF_SMEM: launch_getrf_smem(nb, D.getrf + st.off, st.count, st.smem); break;
+        case K_GETRF_DENSE: launch_getrf_dense(nb, D.getrf + st.off, st.count); break;
         case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count); break;
         case -1:
             for (size_t k = st.off; k < st.off + st.count; ++k)
@@ -689,6 +799,9 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "dense_threshold")) return &g.opt.dense_threshold;
     if (!strcmp(key, "ssssm_mode")) return &g.opt.ssssm_mode;
     if (!strcmp(key, "profile")) return &g.opt.profile;
+    if (!strcmp(key, "getrf_mode")) return &g.opt.getrf_mode;
+    if (!strcmp(key, "tile_variant")) return &g.opt.tile_variant;
+    if (!strcmp(key, "split_pairs")) return &g.opt.split_pairs;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)

@@ -21,6 +21,12 @@ namespace psm {
 
 __device__ __forceinline__ u32 col_begin(const u32* ptr, int j) { return j == 0 ? 0u : ptr[j]; }
 
+// x -= v with a global-memory reduction (several CTAs updating one destination)
+__device__ __forceinline__ void red_sub(double* a, double v) { atomicAdd(a, -v); }
+__device__ __forceinline__ void red_sub(float* a, float v) { atomicAdd(a, -v); }
+__device__ __forceinline__ void red_sub(pangulu_sm100_c64* a, pangulu_sm100_c64 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
+__device__ __forceinline__ void red_sub(pangulu_sm100_c32* a, pangulu_sm100_c32 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
+
 // ------------------------------------------------------------------------------------------------
 // SSSSM, sparse path.  grid = (#destinations x column groups); one warp owns one column j of the
 // destination and applies EVERY operand pair queued for that destination (ascending elimination
@@ -162,46 +168,38 @@ panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_pe
 //   smem = 4 * nb * sizeof(T)
 // ------------------------------------------------------------------------------------------------
 template <class T, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-getrf_sparse_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
+__device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, const u16* lidx, T* uval, const u32* uptr, const u16* uidx, T* buf)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* buf = reinterpret_cast<T*>(smem_raw);  // [2][2][nb] : parity x {lcol, urow}
-    const GetrfTask<T> G = tasks[blockIdx.x];
-    const Blk<T> Lo = G.lower, Up = G.upper;
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
     constexpr int NW = THREADS / PSM_WARP;
-
-    for (int i = tid; i < 4 * nb; i += THREADS) buf[i] = zero<T>();
-    __syncthreads();
-
     int prev_level = -1, step = 0;
     for (int level = 0; level < nb; ++level)
     {
-        const u32 u0 = col_begin(Up.ptr, level), u1 = Up.ptr[level + 1];
+        const u32 u0 = col_begin(uptr, level), u1 = uptr[level + 1];
         if (u0 == u1) continue;  // padded row beyond n (pangulu_platform_0100000.c:74-77)
-        const u32 l0 = col_begin(Lo.ptr, level), l1 = Lo.ptr[level + 1];
+        const u32 l0 = col_begin(lptr, level), l1 = lptr[level + 1];
+        if (l0 == l1 && u1 - u0 == 1) continue;  // only the pivot: nothing to scale, nothing to update
         const int par = (step++) & 1;  // parity of the processed-level count: skipped rows do not flip it
         T* lcol = buf + (size_t)(par * 2) * nb;
         T* urow = lcol + nb;
-        const T piv = clamp_pivot(Up.val[u0]);
+        const T piv = clamp_pivot(uval[u0]);
         for (u32 e = l0 + tid; e < l1; e += THREADS)
         {
-            const T v = vdiv(Lo.val[e], piv);
-            Lo.val[e] = v;
-            lcol[Lo.idx[e]] = v;
+            const T v = vdiv(lval[e], piv);
+            lval[e] = v;
+            lcol[lidx[e]] = v;
         }
-        for (u32 e = u0 + 1 + tid; e < u1; e += THREADS) urow[Up.idx[e]] = Up.val[e];
+        for (u32 e = u0 + 1 + tid; e < u1; e += THREADS) urow[uidx[e]] = uval[e];
         // clear the OTHER parity's vectors (used by prev_level; all its readers passed the barrier
         // that ended that level)
         if (prev_level >= 0)
         {
             T* plcol = buf + (size_t)((par ^ 1) * 2) * nb;
             T* purow = plcol + nb;
-            const u32 pl0 = col_begin(Lo.ptr, prev_level), pl1 = Lo.ptr[prev_level + 1];
-            const u32 pu0 = col_begin(Up.ptr, prev_level), pu1 = Up.ptr[prev_level + 1];
-            for (u32 e = pl0 + tid; e < pl1; e += THREADS) plcol[Lo.idx[e]] = zero<T>();
-            for (u32 e = pu0 + 1 + tid; e < pu1; e += THREADS) purow[Up.idx[e]] = zero<T>();
+            const u32 pl0 = col_begin(lptr, prev_level), pl1 = lptr[prev_level + 1];
+            const u32 pu0 = col_begin(uptr, prev_level), pu1 = uptr[prev_level + 1];
+            for (u32 e = pl0 + tid; e < pl1; e += THREADS) plcol[lidx[e]] = zero<T>();
+            for (u32 e = pu0 + 1 + tid; e < pu1; e += THREADS) purow[uidx[e]] = zero<T>();
         }
         __syncthreads();
 
@@ -210,32 +208,215 @@ getrf_sparse_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
         {
             if (it < nrow)
             {
-                const int r = Lo.idx[l0 + it];
+                const int r = lidx[l0 + it];
                 const T lr = lcol[r];
-                const u32 r0 = col_begin(Up.ptr, r), r1 = Up.ptr[r + 1];
+                const u32 r0 = col_begin(uptr, r), r1 = uptr[r + 1];
                 for (u32 q = r0 + lane; q < r1; q += PSM_WARP)
                 {
-                    T v = Up.val[q];
-                    fnma(v, lr, urow[Up.idx[q]]);
-                    Up.val[q] = v;
+                    T v = uval[q];
+                    fnma(v, lr, urow[uidx[q]]);
+                    uval[q] = v;
                 }
             }
             else
             {
                 const u32 eu = u0 + 1 + (it - nrow);
-                const int c = Up.idx[eu];
+                const int c = uidx[eu];
                 const T uc = urow[c];
-                const u32 q0 = col_begin(Lo.ptr, c), q1 = Lo.ptr[c + 1];
+                const u32 q0 = col_begin(lptr, c), q1 = lptr[c + 1];
                 for (u32 q = q0 + lane; q < q1; q += PSM_WARP)
                 {
-                    T v = Lo.val[q];
-                    fnma(v, lcol[Lo.idx[q]], uc);
-                    Lo.val[q] = v;
+                    T v = lval[q];
+                    fnma(v, lcol[lidx[q]], uc);
+                    lval[q] = v;
                 }
             }
         }
         __syncthreads();
         prev_level = level;
+    }
+}
+
+// variant 1: the block stays in global memory (L2); used when it does not fit in shared memory
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+getrf_sparse_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* buf = reinterpret_cast<T*>(smem_raw);  // [2][2][nb] : parity x {lcol, urow}
+    const GetrfTask<T> G = tasks[blockIdx.x];
+    for (int i = threadIdx.x; i < 4 * nb; i += THREADS) buf[i] = zero<T>();
+    __syncthreads();
+    getrf_body<T, THREADS>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf);
+}
+
+// variant 2: the whole block (values, pointers, indices of both halves) is staged in shared memory, so a
+// level costs shared-memory latency instead of L2 round trips -- the diagonal blocks sit on the critical
+// path of the factorisation (one GETRF per block row, chained).
+//   smem = (4 nb + nnzL + nnzU) sizeof(T) + 8 (nb+1) + 2 (nnzL + nnzU), rounded; chosen per launch as the
+//   maximum over the batch
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GetrfTask<T> G = tasks[blockIdx.x];
+    const int tid = threadIdx.x;
+    const u32 nl = G.lower.ptr[nb], nu = G.upper.ptr[nb];
+    T* buf = reinterpret_cast<T*>(smem_raw);
+    T* lval = buf + 4 * nb;
+    T* uval = lval + nl;
+    u32* lptr = reinterpret_cast<u32*>(uval + nu);
+    u32* uptr = lptr + (nb + 1);
+    u16* lidx = reinterpret_cast<u16*>(uptr + (nb + 1));
+    u16* uidx = lidx + nl;
+    for (int i = tid; i < 4 * nb; i += THREADS) buf[i] = zero<T>();
+    for (u32 i = tid; i < nl; i += THREADS) { lval[i] = G.lower.val[i]; lidx[i] = G.lower.idx[i]; }
+    for (u32 i = tid; i < nu; i += THREADS) { uval[i] = G.upper.val[i]; uidx[i] = G.upper.idx[i]; }
+    for (int i = tid; i <= nb; i += THREADS) { lptr[i] = i == 0 ? 0u : G.lower.ptr[i]; uptr[i] = i == 0 ? 0u : G.upper.ptr[i]; }
+    __syncthreads();
+    getrf_body<T, THREADS>(nb, lval, lptr, lidx, uval, uptr, uidx, buf);
+    __syncthreads();
+    for (u32 i = tid; i < nl; i += THREADS) G.lower.val[i] = lval[i];
+    for (u32 i = tid; i < nu; i += THREADS) G.upper.val[i] = uval[i];
+}
+
+// variant 3: dense-promoted GETRF for diagonal blocks too full for variant 2 (the separators' blocks).
+// The block is expanded into a column-major nb x nb tile in an L2-resident global scratch, factored by ONE
+// CTA with a blocked right-looking LU (panel width 16: panel columns live in registers one row per thread,
+// one barrier per eliminated column; U12 by forward substitution one column per thread; trailing update
+// with a 4x4 register tile per thread from shared-memory copies of the panel), and the entries of the
+// pattern are gathered back.  Structural zeros stay exact zeros (they only ever receive 0*x), and every
+// entry sees the same sequence "divide by the clamped pivot, then x -= l*u in ascending level order" as in
+// the sparse variants, so the three GETRF kernels agree bit for bit.
+//   smem = 2 * 16 * nbp * sizeof(T) + 64 * sizeof(T), nbp = nb rounded up to 32;  scratch = nbp*nbp*sizeof(T) per task
+#define PSM_GETRF_W 16
+template <class T>
+__global__ void __launch_bounds__(256)
+getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict__ scratch_all)
+{
+    constexpr int W = PSM_GETRF_W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbp = (nb + 31) & ~31;
+    T* Ls = reinterpret_cast<T*>(smem_raw);   // [W][nbp]  L panel (rows >= j0)
+    T* Us = Ls + W * nbp;                     // [W][nbp]  U12 rows of the panel
+    T* urow = Us + W * nbp;                   // [2][W+...] pivot row of the current column, double buffered
+    const GetrfTask<T> G = tasks[blockIdx.x];
+    const Blk<T> Lo = G.lower, Up = G.upper;
+    T* Tm = scratch_all + (size_t)blockIdx.x * nbp * nbp;  // column major, leading dimension nbp
+    const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
+
+    // ---- expand: zero, then scatter the strict-lower CSC half and the upper CSR half
+    for (int i = tid; i < nbp * nbp; i += 256) Tm[i] = zero<T>();
+    __syncthreads();
+    for (int c = warp; c < nb; c += 8)
+    {
+        for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)c * nbp + Lo.idx[e]] = Lo.val[e];
+        for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)Up.idx[e] * nbp + c] = Up.val[e];  // row c of U
+    }
+    __syncthreads();
+
+    const int r = tid;  // this thread's row in the panel phase
+    for (int j0 = 0; j0 < nb; j0 += W)
+    {
+        const int w = min(W, nb - j0);
+        // ---- panel: columns j0 .. j0+w-1, rows j0 .. nb-1, one row per thread in registers
+        T p[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) p[q] = (q < w && r >= j0 && r < nb) ? Tm[(size_t)(j0 + q) * nbp + r] : zero<T>();
+#pragma unroll
+        for (int jj = 0; jj < W; ++jj)
+        {
+            if (jj < w)
+            {
+                const int l = j0 + jj;
+                T* ur = urow + (jj & 1) * W;
+                if (r == l)
+                {
+#pragma unroll
+                    for (int q = 0; q < W; ++q) ur[q] = p[q];
+                }
+                __syncthreads();
+                if (r > l && r < nb)
+                {
+                    const T piv = clamp_pivot(ur[jj]);
+                    p[jj] = vdiv(p[jj], piv);
+#pragma unroll
+                    for (int q = 0; q < W; ++q)
+                        if (q > jj) fnma(p[q], p[jj], ur[q]);
+                }
+            }
+        }
+        // publish the panel (L part below the diagonal of each column, U part above) to memory and to Ls
+        if (r >= j0 && r < nb)
+        {
+#pragma unroll
+            for (int q = 0; q < W; ++q)
+                if (q < w) { Tm[(size_t)(j0 + q) * nbp + r] = p[q]; Ls[q * nbp + r] = p[q]; }
+        }
+        __syncthreads();
+        const int t0 = j0 + w;  // first trailing row/column
+        if (t0 >= nb) break;
+        // ---- U12 = L11^-1 T12: one trailing column per thread, forward substitution over the w panel rows
+        for (int c = t0 + tid; c < nb; c += 256)
+        {
+            T u[W];
+#pragma unroll
+            for (int q = 0; q < W; ++q) u[q] = q < w ? Tm[(size_t)c * nbp + j0 + q] : zero<T>();
+#pragma unroll
+            for (int q = 1; q < W; ++q)
+#pragma unroll
+                for (int s2 = 0; s2 < W; ++s2)
+                    if (s2 < q && q < w) fnma(u[q], Ls[s2 * nbp + j0 + q], u[s2]);
+#pragma unroll
+            for (int q = 0; q < W; ++q)
+                if (q < w) { Tm[(size_t)c * nbp + j0 + q] = u[q]; Us[q * nbp + c] = u[q]; }
+        }
+        __syncthreads();
+        // ---- trailing update T22 -= L21 U12, 4x4 register tile per thread: rows lane + 32 i, columns warp + 8 j
+        for (int cb = t0; cb < nb; cb += 32)
+            for (int rb = t0; rb < nb; rb += 128)
+            {
+                T acc[4][4];
+                int rr[4], cc[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rr[i] = rb + lane + 32 * i;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) cc[j] = cb + warp + 8 * j;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = (rr[i] < nb && cc[j] < nb) ? Tm[(size_t)cc[j] * nbp + rr[i]] : zero<T>();
+#pragma unroll
+                for (int q = 0; q < W; ++q)
+                {
+                    if (q < w)
+                    {
+                        T lv[4], uv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) lv[i] = rr[i] < nbp ? Ls[q * nbp + rr[i]] : zero<T>();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) uv[j] = cc[j] < nbp ? Us[q * nbp + cc[j]] : zero<T>();
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) fnma(acc[i][j], lv[i], uv[j]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (rr[i] < nb && cc[j] < nb) Tm[(size_t)cc[j] * nbp + rr[i]] = acc[i][j];
+            }
+        __syncthreads();
+    }
+    __syncthreads();
+    // ---- gather the pattern back
+    for (int c = warp; c < nb; c += 8)
+    {
+        for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Lo.val[e] = Tm[(size_t)c * nbp + Lo.idx[e]];
+        for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Up.val[e] = Tm[(size_t)Up.idx[e] * nbp + c];
     }
 }
 
@@ -545,6 +726,233 @@ ssssm_tile_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPai
                 const int c = D.u.idx[e];
                 if (c >= c0 + ncol) break;
                 vsub(D.u.val[e], Cs[(c - c0) * LDA + r]);
+            }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// SSSSM dense-tile path, pipelined variant (the default).  Same tiling idea as ssssm_tile_kernel, but:
+//  * 512 threads (16 warps): one warp gathers one of the 16 A columns of a chunk, 16 threads gather one
+//    of the 32 B columns; warp grid (TM/32) x (16/(TM/32)) for the DMMA phase;
+//  * the CSC entries of chunk i+1 are fetched into REGISTERS before the DMMA phase of chunk i and
+//    scattered into the other shared-memory buffer afterwards, so L2 latency hides behind the tensor
+//    work instead of sitting between two barriers;
+//  * a destination may be split over several CTAs by operand-pair range (flags & 1): those CTAs
+//    subtract their partial product with FP64 global reductions instead of plain read-modify-write.
+//   smem = max(2 * 16 * (TM+4 + 36), 32 * (TM+4)) * sizeof(T)
+// ------------------------------------------------------------------------------------------------
+template <class T, int TM>
+__global__ void __launch_bounds__(512, 1)
+ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int tiles_per_dest)
+{
+    static_assert(TM == 128 || TM == 256, "tile height");
+    constexpr int TN = PSM_TILE_N, KC = PSM_TILE_K;
+    constexpr int LDA = TM + 4, LDB = TN + 4;
+    constexpr int WM = TM / 32, WN = 16 / WM, WTN = TN / WN, NT = WTN / 8;
+    constexpr int AR = TM / 32;  // A entries per lane per chunk column
+    constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);
+    T* As0 = sm;
+    T* Bs0 = sm + 2 * KC * LDA;
+    T* Cs = sm;
+
+    const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
+    const int d = blockIdx.x / tiles_per_dest;
+    const int c0 = (blockIdx.x % tiles_per_dest) * TN;
+    const SsssmDest<T> D = dests[d];
+    const bool diag = D.u.val != nullptr;
+    const int ncol = min(TN, nb - c0);
+    if (!diag && col_begin(D.c.ptr, c0) == D.c.ptr[c0 + ncol]) return;
+
+    constexpr int NACC = kDouble ? (4 * NT * 2) : (TM / 32) * 2;
+    T acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = zero<T>();
+    const int wm = warp % WM, wn = warp / WM;
+    const int m_base = wm * 32, n_base = wn * WTN;
+
+    for (int i = tid; i < 2 * KC * (LDA + LDB); i += 512) sm[i] = zero<T>();
+
+    // ---- fetch stage state -----------------------------------------------------------------------------
+    const int b_jj = tid / 16, b_l = tid % 16;
+    const int b_col = c0 + b_jj;
+    const unsigned grp_shift = (lane / 16) * 16;
+    u32 p = D.pair_begin;
+    int k0 = 0;
+    BlkRO<T> A, B;
+    u32 cur = 0, bend = 0;
+    u16 aidx[AR];
+    T aval[AR];
+    int brow = -1;
+    T bval = zero<T>();
+    auto load_pair = [&]() {
+        A = pairs[p].a;
+        B = pairs[p].b;
+        cur = 0;
+        bend = 0;
+        if (b_jj < ncol) { cur = col_begin(B.ptr, b_col); bend = B.ptr[b_col + 1]; }
+    };
+    // advance to the next chunk whose A columns are not all empty and pull its entries into registers
+    auto fetch = [&]() -> bool {
+        for (;;)
+        {
+            if (k0 >= nb)
+            {
+                ++p;
+                k0 = 0;
+                if (p >= D.pair_end) return false;
+                load_pair();
+            }
+            const int kc = min(KC, nb - k0);
+            const bool a_has = A.ptr[k0 + kc] > col_begin(A.ptr, k0);
+            {
+                const u32 e = cur + b_l;
+                bool in = false;
+                int r = 0;
+                if (e < bend) { r = B.idx[e]; in = r < k0 + kc; }
+                brow = -1;
+                if (a_has && in) { bval = B.val[e]; brow = r - k0; }
+                const unsigned m = __ballot_sync(PSM_FULL, in);
+                cur += __popc((m >> grp_shift) & 0xffffu);
+            }
+            if (a_has)
+            {
+                u32 a0 = 0, a1 = 0;
+                if (warp < kc) { a0 = col_begin(A.ptr, k0 + warp); a1 = A.ptr[k0 + warp + 1]; }
+#pragma unroll
+                for (int i = 0; i < AR; ++i)
+                {
+                    const u32 e = a0 + lane + 32 * i;
+                    aidx[i] = 0xffff;
+                    if (e < a1) { aidx[i] = A.idx[e]; aval[i] = A.val[e]; }
+                }
+                k0 += KC;
+                return true;
+            }
+            k0 += KC;
+        }
+    };
+
+    bool more = false;
+    if (p < D.pair_end) { load_pair(); more = fetch(); }
+    __syncthreads();
+    int it = 0;
+    while (more)
+    {
+        const int buf = it & 1;
+        T* As = As0 + buf * KC * LDA;
+        T* Bs = Bs0 + buf * KC * LDB;
+        {
+            T* Ak = As + warp * LDA;
+#pragma unroll
+            for (int i = 0; i < AR; ++i)
+                if (aidx[i] != 0xffff) Ak[aidx[i]] = aval[i];
+            if (brow >= 0) Bs[brow * LDB + b_jj] = bval;
+        }
+        __syncthreads();
+        more = fetch();  // loads of the next chunk stay in flight during the tensor phase below
+        {
+            T* Ao = As0 + (buf ^ 1) * KC * LDA;
+            T* Bo = Bs0 + (buf ^ 1) * KC * LDB;
+            for (int i = tid; i < KC * LDA; i += 512) Ao[i] = zero<T>();
+            for (int i = tid; i < KC * LDB; i += 512) Bo[i] = zero<T>();
+        }
+        if constexpr (kDouble)
+        {
+            const int lr = lane / 4, lk = lane % 4;
+#pragma unroll
+            for (int k4 = 0; k4 < KC; k4 += 4)
+            {
+                double a[4], b[NT];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) a[mt] = As[(k4 + lk) * LDA + m_base + mt * 8 + lr];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) b[nt] = Bs[(k4 + lk) * LDB + n_base + nt * 8 + lr];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[(mt * NT + nt) * 2], acc[(mt * NT + nt) * 2 + 1], a[mt], b[nt]);
+            }
+        }
+        else
+        {
+            // FMA register tile: thread (tx, ty) owns rows tx + 32 i (i < TM/32) and columns 2 ty, 2 ty + 1
+            const int tx = tid % 32, ty = tid / 32;
+#pragma unroll 4
+            for (int kk = 0; kk < KC; ++kk)
+            {
+                const T b0 = Bs[kk * LDB + ty * 2], b1 = Bs[kk * LDB + ty * 2 + 1];
+#pragma unroll
+                for (int i = 0; i < TM / 32; ++i)
+                {
+                    const T av = As[kk * LDA + tx + 32 * i];
+                    fma_acc(acc[i * 2], av, b0);
+                    fma_acc(acc[i * 2 + 1], av, b1);
+                }
+            }
+        }
+        __syncthreads();
+        ++it;
+    }
+
+    // epilogue: accumulator -> shared memory (column major [TN][LDA]) -> destination pattern
+    __syncthreads();
+    if constexpr (kDouble)
+    {
+        const int lr = lane / 4, lc = (lane % 4) * 2;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt)
+            {
+                const int r = m_base + mt * 8 + lr, c = n_base + nt * 8 + lc;
+                Cs[c * LDA + r] = acc[(mt * NT + nt) * 2];
+                Cs[(c + 1) * LDA + r] = acc[(mt * NT + nt) * 2 + 1];
+            }
+    }
+    else
+    {
+        const int tx = tid % 32, ty = tid / 32;
+#pragma unroll
+        for (int i = 0; i < TM / 32; ++i)
+        {
+            Cs[(ty * 2) * LDA + tx + 32 * i] = acc[i * 2];
+            Cs[(ty * 2 + 1) * LDA + tx + 32 * i] = acc[i * 2 + 1];
+        }
+    }
+    __syncthreads();
+    const bool shared_dest = (D.flags & 1u) != 0;
+    for (int jj = warp; jj < ncol; jj += 16)
+    {
+        const int j = c0 + jj;
+        const u32 e0 = col_begin(D.c.ptr, j), e1 = D.c.ptr[j + 1];
+        const T* Cj = Cs + jj * LDA;
+        if (shared_dest)
+            for (u32 e = e0 + lane; e < e1; e += PSM_WARP) red_sub(&D.c.val[e], Cj[D.c.idx[e]]);
+        else
+            for (u32 e = e0 + lane; e < e1; e += PSM_WARP) vsub(D.c.val[e], Cj[D.c.idx[e]]);
+    }
+    if (diag)
+    {
+        for (int r = tid; r < min(nb, c0 + ncol); r += 512)
+        {
+            const u32 r0 = col_begin(D.u.ptr, r), r1 = D.u.ptr[r + 1];
+            u32 lo = r0, hi = r1;
+            while (lo < hi)
+            {
+                const u32 mid = (lo + hi) >> 1;
+                if ((int)D.u.idx[mid] < c0) lo = mid + 1;
+                else hi = mid;
+            }
+            for (u32 e = lo; e < r1; ++e)
+            {
+                const int c = D.u.idx[e];
+                if (c >= c0 + ncol) break;
+                if (shared_dest) red_sub(&D.u.val[e], Cs[(c - c0) * LDA + r]);
+                else vsub(D.u.val[e], Cs[(c - c0) * LDA + r]);
             }
         }
     }

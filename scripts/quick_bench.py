@@ -8,10 +8,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--case", default="p3"); ap.add_argument("--size", type=int, default=32)
 ap.add_argument("--nb", type=int, default=128); ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--mode", type=int, default=1); ap.add_argument("--profile", type=int, default=1)
-ap.add_argument("--opt", action="append", default=[])
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--schedule", type=int, default=1)
 a = ap.parse_args()
 A = {"p3": matrices.poisson3d, "p2": matrices.laplace2d, "s27": matrices.stencil27}[a.case](a.size)
-t = time.time(); s = PanguLU(A, nb=a.nb, mode=a.mode); t_init = time.time() - t
+t = time.time(); s = PanguLU(A, nb=a.nb, mode=a.mode, schedule=a.schedule); t_init = time.time() - t
 L = s.L
 for kv in a.opt:
     k, v = kv.split("="); L.pangulu_sm100_set_option(k.encode(), int(v))

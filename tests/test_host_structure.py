@@ -66,12 +66,13 @@ def test_structure_matches_live_reference(make, nb):
         s.finalize()
 
 
-def test_schedule_respects_dependencies():
-    """Every task of the static schedule runs in a later wave than the tasks that produce its operands, and all
-    updates of a destination sit in the wave that finalises it."""
+@pytest.mark.parametrize("policy", [0, 1], ids=["lazy", "eager"])
+def test_schedule_respects_dependencies(policy):
+    """Every task of the static schedule runs in a later wave than the tasks that produce its operands, and no
+    update of a destination runs after the wave that finalises it (lazy policy: exactly in that wave)."""
     A = matrices.poisson3d(12)
     nb = 32
-    s = PanguLU(A, nb=nb, host_only=True)
+    s = PanguLU(A, nb=nb, host_only=True, schedule=policy)
     try:
         tasks, wave_ptr = s.schedule()
         wave_of_task = np.repeat(np.arange(len(wave_ptr) - 1), np.diff(wave_ptr.astype(np.int64)))
@@ -92,7 +93,11 @@ def test_schedule_respects_dependencies():
                 assert final[diag_lower] < w
             if t["kernel_id"] == _lib.TASK_SSSSM:
                 assert final[int(t["op1"])] < w and final[int(t["op2"])] < w
-                assert final[int(t["opdst"])] == w  # applied in the wave that finalises the destination
+                if policy == 0:
+                    assert final[int(t["opdst"])] == w  # applied in the wave that finalises the destination
+                else:
+                    assert w <= final[int(t["opdst"])]
+                    assert w == 1 + max(final[int(t["op1"])], final[int(t["op2"])])  # as early as possible
                 n_upd += 1
         assert n_upd == int(s.info("n_ssssm")) and n_upd > 0
         # within a wave: SSSSM first, then GETRF, then TSTRF/GESSM

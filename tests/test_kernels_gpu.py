@@ -243,3 +243,42 @@ def test_empty_and_padded_blocks():
         assert rel_err(D.fetch(s_lo, len(lo.value)), want_lo.value) <= 1e-12
     finally:
         D.close()
+
+
+@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64"])
+@pytest.mark.parametrize("getrf_mode", [1, 0, 3], ids=["global-sparse", "smem-staged", "dense-promoted"])
+@pytest.mark.parametrize("make,nb", [(lambda: matrices.poisson3d(10), 64), (lambda: matrices.stencil27(7), 200), (lambda: matrices.laplace2d(21), 256)],
+                         ids=["poisson3d-10-nb64", "stencil27-7-nb200", "laplace2d-21-nb256-padded"])
+def test_getrf_variants(make, nb, getrf_mode, vtype):
+    """The three GETRF kernels (global-memory sparse, shared-memory staged, dense-promoted blocked LU) against the
+    oracle on every diagonal block of a matrix, values randomised."""
+    dtype = _lib.VALUE_DTYPES[vtype]
+    L = _lib.load(vtype)
+    blocks = blocks_of(make(), nb, vtype)
+    rng = np.random.default_rng(99)
+    _randomise(blocks, rng, dtype)
+    _, diag = _index(blocks)
+    O = _oracle(vtype)
+    D = DeviceBlocks(vtype, nb)
+    L.pangulu_sm100_set_option(b"getrf_mode", getrf_mode)
+    try:
+        tasks, slots, want = [], [], []
+        for k in sorted(diag):
+            lo, up = diag[k]
+            wl, wu = copy.deepcopy(lo), copy.deepcopy(up)
+            O.getrf(nb, wl, wu)
+            s_lo, s_up = D.slot(lo), D.slot(up)
+            D.link(s_lo, s_up)
+            slots.append((s_lo, s_up, len(lo.value), len(up.value)))
+            want.append((wl, wu))
+            tasks.append(_lib.Task(row=k, col=k, kernel_id=_lib.TASK_GETRF, task_level=k, opdst=C.addressof(s_lo)))
+        arr = (_lib.Task * len(tasks))(*tasks)
+        D.P("hybrid_batched")(nb, len(tasks), C.addressof(arr))  # all diagonal blocks in ONE batched launch
+        D.P("synchronize")()
+        tol = TOL[vtype] * 4
+        for (s_lo, s_up, nl, nu), (wl, wu) in zip(slots, want):
+            assert rel_err(D.fetch(s_lo, nl), wl.value) <= tol
+            assert rel_err(D.fetch(s_up, nu), wu.value) <= tol
+    finally:
+        L.pangulu_sm100_set_option(b"getrf_mode", 0)
+        D.close()
