@@ -11,10 +11,11 @@ ap.add_argument("--mode", type=int, default=1); ap.add_argument("--profile", typ
 ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--schedule", type=int, default=1)
 a = ap.parse_args()
 A = {"p3": matrices.poisson3d, "p2": matrices.laplace2d, "s27": matrices.stencil27}[a.case](a.size)
+from pangulu_b200 import _lib
+L = _lib.load("r64")
+for kv in a.opt:  # platform options must be in place before the plan is built
+    k, v = kv.split("="); assert L.pangulu_sm100_set_option(k.encode(), int(v)) == 0, k
 t = time.time(); s = PanguLU(A, nb=a.nb, mode=a.mode, schedule=a.schedule); t_init = time.time() - t
-L = s.L
-for kv in a.opt:
-    k, v = kv.split("="); L.pangulu_sm100_set_option(k.encode(), int(v))
 print(f"n={A.shape[0]} nnz={A.nnz} nb={a.nb} init {t_init:.2f}s  " + " ".join(f"{k}={s.info('time_'+k):.2f}" for k in ("reorder","symbolic","blocks","schedule","work_model")))
 print(f"symbolic_nnz={s.info('symbolic_nnz'):.3e} nwave={int(s.info('nwave'))} ntask={int(s.info('ntask'))} ssssm={int(s.info('n_ssssm'))} flop={s.info('flop'):.4e} value_MB={s.info('value_bytes')/1e6:.1f}")
 for it in range(a.steps):
