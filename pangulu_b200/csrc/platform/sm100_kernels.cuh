@@ -36,24 +36,26 @@ __device__ __forceinline__ void red_sub(pangulu_sm100_c32* a, pangulu_sm100_c32 
 // Algorithmic HBM bytes per pair: nnzA(sv+si) + nnzB(sv+si) + nnzC(2sv+si) + 3P; applying
 // all pairs of a destination in one pass reads/writes C once per batch instead of once per pair.
 // ------------------------------------------------------------------------------------------------
-template <class T, int WARPS>
-__global__ void __launch_bounds__(WARPS * PSM_WARP)
-ssssm_sparse_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int groups_per_dest)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* acc_all = reinterpret_cast<T*>(smem_raw);
-    const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP;
-    const int d = blockIdx.x / groups_per_dest;
-    const int j = (blockIdx.x % groups_per_dest) * WARPS + warp;
-    if (j >= nb) return;
-    T* acc = acc_all + (size_t)warp * nb;
-    const SsssmDest<T> D = dests[d];
+// warp shuffles of a value of type T
+__device__ __forceinline__ double shfl_v(double v, int src) { return __shfl_sync(PSM_FULL, v, src); }
+__device__ __forceinline__ float shfl_v(float v, int src) { return __shfl_sync(PSM_FULL, v, src); }
+__device__ __forceinline__ pangulu_sm100_c64 shfl_v(pangulu_sm100_c64 v, int src)
+{ pangulu_sm100_c64 r; r.re = __shfl_sync(PSM_FULL, v.re, src); r.im = __shfl_sync(PSM_FULL, v.im, src); return r; }
+__device__ __forceinline__ pangulu_sm100_c32 shfl_v(pangulu_sm100_c32 v, int src)
+{ pangulu_sm100_c32 r; r.re = __shfl_sync(PSM_FULL, v.re, src); r.im = __shfl_sync(PSM_FULL, v.im, src); return r; }
 
-    // nothing to do for an empty destination column (a padded edge column, or a column of C that
-    // holds no entry in either half)
+// One warp, one destination column j: acc (nb entries of shared memory, owned by the warp) <- sum over the
+// pairs of A * B(:,j), then C(:,j) -= acc on the pattern.  The B entries of the column are read 32 at a time
+// (index, value and the extent of the matching A column per lane) and walked with shuffles, and the first
+// 32 entries of the NEXT A column are loaded before the current one is accumulated, so a step costs one
+// shared-memory round trip instead of a chain of dependent L2 loads.
+template <class T>
+__device__ __forceinline__ void ssssm_sparse_column(int nb, const SsssmDest<T>& D, const SsssmPair<T>* __restrict__ pairs, int j, T* acc, bool atomic)
+{
+    const int lane = threadIdx.x % PSM_WARP;
     const u32 c0 = col_begin(D.c.ptr, j), c1 = D.c.ptr[j + 1];
     const bool diag = D.u.val != nullptr;
-    if (!diag && c0 == c1) return;
+    if (!diag && c0 == c1) return;  // empty destination column (padding, or nothing stored there)
 
     for (int i = lane; i < nb; i += PSM_WARP) acc[i] = zero<T>();
     __syncwarp();
@@ -62,18 +64,49 @@ ssssm_sparse_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmP
     {
         const BlkRO<T> A = pairs[p].a, B = pairs[p].b;
         const u32 b0 = col_begin(B.ptr, j), b1 = B.ptr[j + 1];
-        for (u32 e = b0; e < b1; ++e)
+        for (u32 eb = b0; eb < b1; eb += PSM_WARP)
         {
-            const int k = B.idx[e];
-            const T bv = B.val[e];
-            const u32 a0 = col_begin(A.ptr, k), a1 = A.ptr[k + 1];
-            for (u32 t = a0 + lane; t < a1; t += PSM_WARP) fma_acc(acc[A.idx[t]], A.val[t], bv);
-            __syncwarp();
+            const u32 e = eb + lane;
+            T bv = zero<T>();
+            u32 a0 = 0, a1 = 0;
+            if (e < b1)
+            {
+                const int k = B.idx[e];
+                bv = B.val[e];
+                a0 = col_begin(A.ptr, k);
+                a1 = A.ptr[k + 1];
+            }
+            const int cnt = min((u32)PSM_WARP, b1 - eb);
+            // software pipeline over the B entries of this batch: (ci, cv) = this lane's first entry of the current A column
+            u32 s0 = __shfl_sync(PSM_FULL, a0, 0), s1 = __shfl_sync(PSM_FULL, a1, 0);
+            int ci = -1;
+            T cv = zero<T>();
+            if (s0 + lane < s1) { ci = A.idx[s0 + lane]; cv = A.val[s0 + lane]; }
+            for (int sidx = 0; sidx < cnt; ++sidx)
+            {
+                const T bvs = shfl_v(bv, sidx);
+                u32 n0 = 0, n1 = 0;
+                int ni = -1;
+                T nv = zero<T>();
+                if (sidx + 1 < cnt)
+                {
+                    n0 = __shfl_sync(PSM_FULL, a0, sidx + 1);
+                    n1 = __shfl_sync(PSM_FULL, a1, sidx + 1);
+                    if (n0 + lane < n1) { ni = A.idx[n0 + lane]; nv = A.val[n0 + lane]; }
+                }
+                if (ci >= 0) fma_acc(acc[ci], cv, bvs);
+                for (u32 t = s0 + PSM_WARP + lane; t < s1; t += PSM_WARP) fma_acc(acc[A.idx[t]], A.val[t], bvs);
+                __syncwarp();
+                s0 = n0; s1 = n1; ci = ni; cv = nv;
+            }
         }
     }
 
     // C(:,j) -= acc  (for a diagonal destination D.c is the strict-lower half: rows > j)
-    for (u32 e = c0 + lane; e < c1; e += PSM_WARP) vsub(D.c.val[e], acc[D.c.idx[e]]);
+    if (atomic)
+        for (u32 e = c0 + lane; e < c1; e += PSM_WARP) red_sub(&D.c.val[e], acc[D.c.idx[e]]);
+    else
+        for (u32 e = c0 + lane; e < c1; e += PSM_WARP) vsub(D.c.val[e], acc[D.c.idx[e]]);
     if (diag)
     {
         // upper half is CSR with ascending columns (diagonal first): entry (r, j), r <= j, sits in row r
@@ -89,73 +122,121 @@ ssssm_sparse_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmP
                 if (c < j) lo = mid + 1;
                 else hi = mid;
             }
-            if (lo < D.u.ptr[r + 1] && D.u.idx[lo] == j) vsub(D.u.val[lo], v);
+            if (lo < D.u.ptr[r + 1] && D.u.idx[lo] == j)
+            {
+                if (atomic) red_sub(&D.u.val[lo], v);
+                else vsub(D.u.val[lo], v);
+            }
         }
     }
+    __syncwarp();
+}
+
+template <class T, int WARPS>
+__global__ void __launch_bounds__(WARPS * PSM_WARP)
+ssssm_sparse_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int groups_per_dest)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* acc_all = reinterpret_cast<T*>(smem_raw);
+    const int warp = threadIdx.x / PSM_WARP;
+    const int d = blockIdx.x / groups_per_dest;
+    const int j = (blockIdx.x % groups_per_dest) * WARPS + warp;
+    if (j >= nb) return;
+    const SsssmDest<T> D = dests[d];
+    ssssm_sparse_column<T>(nb, D, pairs, j, acc_all + (size_t)warp * nb, (D.flags & 1u) != 0);
 }
 
 // ------------------------------------------------------------------------------------------------
 // GESSM / TSTRF (sparse triangular panel solves).  grid = (#tasks x row/column groups); one warp
 // owns one column (GESSM) or one row (TSTRF) of B: gather it into a dense shared-memory vector,
 // eliminate entry by entry in index order (lanes sweep the matching column of L / row of U), scatter
-// back.  kind = PANGULU_TASK_GESSM or PANGULU_TASK_TSTRF.
+// back.  kind = PANGULU_TASK_GESSM or PANGULU_TASK_TSTRF.  As in the SSSSM column routine the per-entry
+// metadata (extent of the L column / U row, pivot) is fetched 32 entries at a time and the first 32
+// elements of the next sweep are loaded ahead.
 //   smem = warps * nb * sizeof(T)
 // ------------------------------------------------------------------------------------------------
+template <class T>
+__device__ __forceinline__ void panel_solve_line(int nb, const PanelTask<T>& P, int rc, T* x)
+{
+    const int lane = threadIdx.x % PSM_WARP;
+    const Blk<T> B = P.b, Dg = P.diag;
+    const bool gessm = P.kind == PANGULU_TASK_GESSM;
+    // GESSM: column rc of B (CSC), L = strict-lower CSC of the diagonal block (unit diagonal)
+    // TSTRF: row rc of B through its CSR mirror, U = upper CSR of the diagonal block (diagonal first)
+    const u32* bptr = gessm ? B.ptr : B.rptr;
+    const u16* bidx = gessm ? B.idx : B.ridx;
+    const u32 b0 = col_begin(bptr, rc), b1 = bptr[rc + 1];
+    if (b0 == b1) return;
+    for (int i = lane; i < nb; i += PSM_WARP) x[i] = zero<T>();
+    __syncwarp();
+    if (gessm)
+        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) x[bidx[e]] = B.val[e];
+    else
+        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) x[bidx[e]] = B.val[B.rmap[e]];
+    __syncwarp();
+    const int skip = gessm ? 0 : 1;  // the U row starts with the pivot
+    for (u32 eb = b0; eb < b1; eb += PSM_WARP)
+    {
+        const u32 e = eb + lane;
+        int r = 0;
+        u32 d0 = 0, d1 = 0;
+        T piv = zero<T>();
+        if (e < b1)
+        {
+            r = bidx[e];
+            d0 = col_begin(Dg.ptr, r);
+            d1 = Dg.ptr[r + 1];
+            if (!gessm) piv = clamp_pivot(Dg.val[d0]);
+        }
+        const int cnt = min((u32)PSM_WARP, b1 - eb);
+        u32 s0 = __shfl_sync(PSM_FULL, d0, 0) + skip, s1 = __shfl_sync(PSM_FULL, d1, 0);
+        int ci = -1;
+        T cv = zero<T>();
+        if (s0 + lane < s1) { ci = Dg.idx[s0 + lane]; cv = Dg.val[s0 + lane]; }
+        for (int sidx = 0; sidx < cnt; ++sidx)
+        {
+            const int rs = __shfl_sync(PSM_FULL, r, sidx);
+            u32 n0 = 0, n1 = 0;
+            int ni = -1;
+            T nv = zero<T>();
+            if (sidx + 1 < cnt)
+            {
+                n0 = __shfl_sync(PSM_FULL, d0, sidx + 1) + skip;
+                n1 = __shfl_sync(PSM_FULL, d1, sidx + 1);
+                if (n0 + lane < n1) { ni = Dg.idx[n0 + lane]; nv = Dg.val[n0 + lane]; }
+            }
+            T v = x[rs];
+            if (!gessm)
+            {
+                v = vdiv(v, shfl_v(piv, sidx));
+                __syncwarp();
+                if (lane == 0) x[rs] = v;
+            }
+            if (ci >= 0) fnma(x[ci], v, cv);
+            for (u32 q = s0 + PSM_WARP + lane; q < s1; q += PSM_WARP) fnma(x[Dg.idx[q]], v, Dg.val[q]);
+            __syncwarp();
+            s0 = n0; s1 = n1; ci = ni; cv = nv;
+        }
+    }
+    if (gessm)
+        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[e] = x[bidx[e]];
+    else
+        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[B.rmap[e]] = x[bidx[e]];
+    __syncwarp();
+}
+
 template <class T, int WARPS>
 __global__ void __launch_bounds__(WARPS * PSM_WARP)
 panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_per_task)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* x_all = reinterpret_cast<T*>(smem_raw);
-    const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP;
+    const int warp = threadIdx.x / PSM_WARP;
     const int t = blockIdx.x / groups_per_task;
     const int rc = (blockIdx.x % groups_per_task) * WARPS + warp;
     if (rc >= nb) return;
-    T* x = x_all + (size_t)warp * nb;
     const PanelTask<T> P = tasks[t];
-    const Blk<T> B = P.b, Dg = P.diag;
-
-    if (P.kind == PANGULU_TASK_GESSM)
-    {
-        // column rc of B (CSC); L = strict-lower CSC of the diagonal block, unit diagonal
-        const u32 b0 = col_begin(B.ptr, rc), b1 = B.ptr[rc + 1];
-        if (b0 == b1) return;
-        for (int i = lane; i < nb; i += PSM_WARP) x[i] = zero<T>();
-        __syncwarp();
-        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) x[B.idx[e]] = B.val[e];
-        __syncwarp();
-        for (u32 e = b0; e < b1; ++e)
-        {
-            const int r = B.idx[e];
-            const T v = x[r];
-            const u32 l0 = col_begin(Dg.ptr, r), l1 = Dg.ptr[r + 1];
-            for (u32 q = l0 + lane; q < l1; q += PSM_WARP) fnma(x[Dg.idx[q]], v, Dg.val[q]);
-            __syncwarp();
-        }
-        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[e] = x[B.idx[e]];
-    }
-    else
-    {
-        // row rc of B through its CSR mirror; U = upper CSR of the diagonal block, diagonal first
-        const u32 b0 = col_begin(B.rptr, rc), b1 = B.rptr[rc + 1];
-        if (b0 == b1) return;
-        for (int i = lane; i < nb; i += PSM_WARP) x[i] = zero<T>();
-        __syncwarp();
-        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) x[B.ridx[e]] = B.val[B.rmap[e]];
-        __syncwarp();
-        for (u32 e = b0; e < b1; ++e)
-        {
-            const int c = B.ridx[e];
-            const u32 u0 = col_begin(Dg.ptr, c), u1 = Dg.ptr[c + 1];
-            const T piv = clamp_pivot(Dg.val[u0]);
-            const T v = vdiv(x[c], piv);
-            __syncwarp();
-            if (lane == 0) x[c] = v;
-            for (u32 q = u0 + 1 + lane; q < u1; q += PSM_WARP) fnma(x[Dg.idx[q]], v, Dg.val[q]);
-            __syncwarp();
-        }
-        for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[B.rmap[e]] = x[B.ridx[e]];
-    }
+    panel_solve_line<T>(nb, P, rc, x_all + (size_t)warp * nb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -256,11 +337,8 @@ getrf_sparse_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
 //   smem = (4 nb + nnzL + nnzU) sizeof(T) + 8 (nb+1) + 2 (nnzL + nnzU), rounded; chosen per launch as the
 //   maximum over the batch
 template <class T, int THREADS>
-__global__ void __launch_bounds__(THREADS)
-getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
+__device__ __forceinline__ void getrf_smem_cta(unsigned char* smem_raw, int nb, const GetrfTask<T>& G)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const GetrfTask<T> G = tasks[blockIdx.x];
     const int tid = threadIdx.x;
     const u32 nl = G.lower.ptr[nb], nu = G.upper.ptr[nb];
     T* buf = reinterpret_cast<T*>(smem_raw);
@@ -281,6 +359,15 @@ getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
     for (u32 i = tid; i < nu; i += THREADS) G.upper.val[i] = uval[i];
 }
 
+template <class T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GetrfTask<T> G = tasks[blockIdx.x];
+    getrf_smem_cta<T, THREADS>(smem_raw, nb, G);
+}
+
 // variant 3: dense-promoted GETRF for diagonal blocks too full for variant 2 (the separators' blocks).
 // The block is expanded into a column-major nb x nb tile in an L2-resident global scratch, factored by ONE
 // CTA with a blocked right-looking LU (panel width 16: panel columns live in registers one row per thread,
@@ -291,25 +378,22 @@ getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
 // the sparse variants, so the three GETRF kernels agree bit for bit.
 //   smem = 2 * 16 * nbp * sizeof(T) + 64 * sizeof(T), nbp = nb rounded up to 32;  scratch = nbp*nbp*sizeof(T) per task
 #define PSM_GETRF_W 16
-template <class T>
-__global__ void __launch_bounds__(256)
-getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict__ scratch_all)
+template <class T, int THREADS>
+__device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb, const GetrfTask<T>& G, T* __restrict__ Tm)
 {
     constexpr int W = PSM_GETRF_W;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = THREADS / PSM_WARP;
     const int nbp = (nb + 31) & ~31;
     T* Ls = reinterpret_cast<T*>(smem_raw);   // [W][nbp]  L panel (rows >= j0)
     T* Us = Ls + W * nbp;                     // [W][nbp]  U12 rows of the panel
     T* urow = Us + W * nbp;                   // [2][W+...] pivot row of the current column, double buffered
-    const GetrfTask<T> G = tasks[blockIdx.x];
-    const Blk<T> Lo = G.lower, Up = G.upper;
-    T* Tm = scratch_all + (size_t)blockIdx.x * nbp * nbp;  // column major, leading dimension nbp
+    const Blk<T> Lo = G.lower, Up = G.upper;  // Tm: column major, leading dimension nbp
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
 
     // ---- expand: zero, then scatter the strict-lower CSC half and the upper CSR half
-    for (int i = tid; i < nbp * nbp; i += 256) Tm[i] = zero<T>();
+    for (int i = tid; i < nbp * nbp; i += THREADS) Tm[i] = zero<T>();
     __syncthreads();
-    for (int c = warp; c < nb; c += 8)
+    for (int c = warp; c < nb; c += NW)
     {
         for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)c * nbp + Lo.idx[e]] = Lo.val[e];
         for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)Up.idx[e] * nbp + c] = Up.val[e];  // row c of U
@@ -358,7 +442,7 @@ getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict
         const int t0 = j0 + w;  // first trailing row/column
         if (t0 >= nb) break;
         // ---- U12 = L11^-1 T12: one trailing column per thread, forward substitution over the w panel rows
-        for (int c = t0 + tid; c < nb; c += 256)
+        for (int c = t0 + tid; c < nb; c += THREADS)
         {
             T u[W];
 #pragma unroll
@@ -373,8 +457,8 @@ getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict
                 if (q < w) { Tm[(size_t)c * nbp + j0 + q] = u[q]; Us[q * nbp + c] = u[q]; }
         }
         __syncthreads();
-        // ---- trailing update T22 -= L21 U12, 4x4 register tile per thread: rows lane + 32 i, columns warp + 8 j
-        for (int cb = t0; cb < nb; cb += 32)
+        // ---- trailing update T22 -= L21 U12, 4x4 register tile per thread: rows lane + 32 i, columns warp + NW j
+        for (int cb = t0; cb < nb; cb += 4 * NW)
             for (int rb = t0; rb < nb; rb += 128)
             {
                 T acc[4][4];
@@ -382,7 +466,7 @@ getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rr[i] = rb + lane + 32 * i;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cc[j] = cb + warp + 8 * j;
+                for (int j = 0; j < 4; ++j) cc[j] = cb + warp + NW * j;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -413,11 +497,21 @@ getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict
     }
     __syncthreads();
     // ---- gather the pattern back
-    for (int c = warp; c < nb; c += 8)
+    for (int c = warp; c < nb; c += NW)
     {
         for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Lo.val[e] = Tm[(size_t)c * nbp + Lo.idx[e]];
         for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Up.val[e] = Tm[(size_t)Up.idx[e] * nbp + c];
     }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict__ scratch_all)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbp = (nb + 31) & ~31;
+    const GetrfTask<T> G = tasks[blockIdx.x];
+    getrf_dense_cta<T, 256>(smem_raw, nb, G, scratch_all + (size_t)blockIdx.x * nbp * nbp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -744,8 +838,7 @@ ssssm_tile_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPai
 //   smem = max(2 * 16 * (TM+4 + 36), 32 * (TM+4)) * sizeof(T)
 // ------------------------------------------------------------------------------------------------
 template <class T, int TM>
-__global__ void __launch_bounds__(512, 1)
-ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int tiles_per_dest)
+__device__ __forceinline__ void ssssm_tile2_cta(unsigned char* smem_raw, int nb, const SsssmDest<T>& D, const SsssmPair<T>* __restrict__ pairs, int c0, bool force_atomic)
 {
     static_assert(TM == 128 || TM == 256, "tile height");
     constexpr int TN = PSM_TILE_N, KC = PSM_TILE_K;
@@ -753,16 +846,12 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
     constexpr int WM = TM / 32, WN = 16 / WM, WTN = TN / WN, NT = WTN / 8;
     constexpr int AR = TM / 32;  // A entries per lane per chunk column
     constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sm = reinterpret_cast<T*>(smem_raw);
     T* As0 = sm;
     T* Bs0 = sm + 2 * KC * LDA;
     T* Cs = sm;
 
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
-    const int d = blockIdx.x / tiles_per_dest;
-    const int c0 = (blockIdx.x % tiles_per_dest) * TN;
-    const SsssmDest<T> D = dests[d];
     const bool diag = D.u.val != nullptr;
     const int ncol = min(TN, nb - c0);
     if (!diag && col_begin(D.c.ptr, c0) == D.c.ptr[c0 + ncol]) return;
@@ -924,7 +1013,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
         }
     }
     __syncthreads();
-    const bool shared_dest = (D.flags & 1u) != 0;
+    const bool shared_dest = force_atomic || (D.flags & 1u) != 0;
     for (int jj = warp; jj < ncol; jj += 16)
     {
         const int j = c0 + jj;
@@ -956,6 +1045,17 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
             }
         }
     }
+}
+
+template <class T, int TM>
+__global__ void __launch_bounds__(512, 1)
+ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPair<T>* __restrict__ pairs, int tiles_per_dest)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int d = blockIdx.x / tiles_per_dest;
+    const int c0 = (blockIdx.x % tiles_per_dest) * PSM_TILE_N;
+    const SsssmDest<T> D = dests[d];
+    ssssm_tile2_cta<T, TM>(smem_raw, nb, D, pairs, c0, false);
 }
 
 }  // namespace psm
