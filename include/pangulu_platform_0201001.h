@@ -126,6 +126,9 @@ void pangulu_sm100_plan_execute(pangulu_sm100_plan *plan);
 /* execute waves [w0, w1) only (multi-GPU driver interleaves block exchange between waves) */
 void pangulu_sm100_plan_execute_range(pangulu_sm100_plan *plan, pangulu_uint64_t w0, pangulu_uint64_t w1);
 void pangulu_sm100_plan_destroy(pangulu_sm100_plan *plan);
+/* persistent executor with option "trace" = 1 at plan creation: per task {kind, fetch_ns, start_ns, end_ns}
+ * (4 u64 per task) of the last execution; returns the number of tasks (call with out = NULL to size the buffer) */
+long long pangulu_sm100_plan_trace(pangulu_sm100_plan *plan, unsigned long long *out, long long cap);
 
 /* Instrumentation (bench.py): kernels launched / device time per kernel class since the last reset.
  * cls: 0 getrf, 1 tstrf, 2 gessm, 3 ssssm-sparse, 4 ssssm-tile, 5 copy/aux.  Timing is off unless

@@ -74,6 +74,8 @@ void pangulu_sm100_driver_reset_values(void *handle, int also_device);
 /* resident mode: enqueue the whole factorisation on the module's stream (pangulu_sm100_stream()) without
  * synchronising; <id>_synchronize() or a stream event completes it */
 void pangulu_sm100_driver_gstrf_enqueue(void *handle);
+/* task trace of the last resident gstrf (see pangulu_sm100_plan_trace) */
+long long pangulu_sm100_driver_trace(void *handle, unsigned long long *out, long long cap);
 /* device -> host copy of the owned factors (resident mode) */
 void pangulu_sm100_driver_download(void *handle);
 /* the reference's gstrf self-check ||L(U1) - A1|| / ||A1|| (src/pangulu_numeric.c:1082-1341) on host factors */

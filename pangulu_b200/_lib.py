@@ -29,7 +29,7 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_download_blocks", "pangulu_sm100_upload_blocks",
     "pangulu_sm100_plan_create", "pangulu_sm100_plan_execute", "pangulu_sm100_plan_execute_range",
     "pangulu_sm100_plan_destroy", "pangulu_sm100_stats_reset", "pangulu_sm100_stats_launches",
-    "pangulu_sm100_stats_ms", "pangulu_sm100_stream", "pangulu_sm100_version",
+    "pangulu_sm100_stats_ms", "pangulu_sm100_stream", "pangulu_sm100_version", "pangulu_sm100_plan_trace",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [
@@ -37,6 +37,7 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_config", "pangulu_sm100_driver_info", "pangulu_sm100_driver_slot",
     "pangulu_sm100_driver_perm", "pangulu_sm100_driver_tasks", "pangulu_sm100_driver_reset_values",
     "pangulu_sm100_driver_download", "pangulu_sm100_driver_factor_check", "pangulu_sm100_driver_gstrf_enqueue",
+    "pangulu_sm100_driver_trace",
 ]
 
 
@@ -152,6 +153,10 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_driver_reset_values.argtypes = [vp, C.c_int]
     L.pangulu_sm100_driver_download.argtypes = [vp]
     L.pangulu_sm100_driver_gstrf_enqueue.argtypes = [vp]
+    L.pangulu_sm100_driver_trace.argtypes = [vp, vp, C.c_longlong]
+    L.pangulu_sm100_driver_trace.restype = C.c_longlong
+    L.pangulu_sm100_plan_trace.argtypes = [vp, vp, C.c_longlong]
+    L.pangulu_sm100_plan_trace.restype = C.c_longlong
     L.pangulu_sm100_driver_factor_check.argtypes = [vp]
     L.pangulu_sm100_driver_factor_check.restype = C.c_double
     L.platform = P

@@ -35,6 +35,7 @@ struct DriverConfig
     long long verbose = 0;
     long long host_only = 0;
     long long schedule = 1;
+    long long lookahead = 6;
 };
 DriverConfig g_cfg;
 
@@ -70,6 +71,7 @@ int pangulu_sm100_driver_config(const char* key, long long value)
     else if (k == "verbose") g_cfg.verbose = value;
     else if (k == "host_only") g_cfg.host_only = value;
     else if (k == "schedule") g_cfg.schedule = value;
+    else if (k == "lookahead") g_cfg.lookahead = value;
     else return -1;
     return 0;
 }
@@ -150,6 +152,7 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     std::vector<eidx>().swap(h->S.idx);
     t0 = wall_seconds();
     h->sched.policy = (int)g_cfg.schedule;
+    h->sched.lookahead = (int)g_cfg.lookahead;
     build_schedule(h->B, h->sched);
     h->times["schedule"] = wall_seconds() - t0;
     t0 = wall_seconds();
@@ -349,6 +352,12 @@ void pangulu_sm100_driver_gstrf_enqueue(void* handle)
                                             h->sched.tasks.data());
     pangulu_sm100_plan_execute(h->plan);
     h->factored = true;
+}
+
+long long pangulu_sm100_driver_trace(void* handle, unsigned long long* out, long long cap)
+{
+    Handle* h = (Handle*)handle;
+    return h->plan ? pangulu_sm100_plan_trace(h->plan, out, cap) : 0;
 }
 
 void pangulu_sm100_driver_download(void* handle)

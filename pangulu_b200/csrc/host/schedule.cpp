@@ -126,15 +126,39 @@ void build_schedule(BlockStore& B, Schedule& S)
     //            destination is read and written once, but its updates pile up on the critical path;
     //   policy 1 (eager, right-looking) = 1 + max(depth of its operands), already stored: the update runs as soon
     //            as both panel blocks are final -- wide waves, and only the last update precedes the panel op.
+    //   policy 2 (windowed) = max(eager wave, depth of the destination - lookahead): updates with a lot of slack are
+    //            gathered `lookahead` waves before their destination is finalised (one multi-pair pass, off the
+    //            critical path); the few that become ready inside the window run as soon as they can.  Inside a
+    //            wave the updates are ordered by slack, most urgent first (the persistent executor consumes the
+    //            list in order).
     int32_t nwave = 0;
-    for (auto& t : protos)
+    std::vector<int32_t> slack(protos.size(), 0);
+    for (size_t i = 0; i < protos.size(); ++i)
     {
-        if (t.cls == 0 && S.policy == 0)
+        Proto& t = protos[i];
+        if (t.cls == 0)
         {
-            if (t.row == t.col) t.wave = S.depth_diag[t.row];
-            else t.wave = S.depth_offdiag[B.find_block(t.row, t.col)];
+            const int32_t dd = t.row == t.col ? S.depth_diag[t.row] : S.depth_offdiag[B.find_block(t.row, t.col)];
+            if (S.policy == 0) t.wave = dd;
+            else if (S.policy == 2) t.wave = std::max(t.wave, dd - S.lookahead);
+            slack[i] = dd - t.wave;
         }
         nwave = std::max(nwave, t.wave + 1);
+    }
+    if (S.policy == 2)
+    {
+        // stable order by (wave, class, slack): done through an index sort, then the bucket pass below keeps it
+        std::vector<size_t> ord(protos.size());
+        for (size_t i = 0; i < ord.size(); ++i) ord[i] = i;
+        std::stable_sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
+            if (protos[a].wave != protos[b].wave) return protos[a].wave < protos[b].wave;
+            if (protos[a].cls != protos[b].cls) return protos[a].cls < protos[b].cls;
+            return slack[a] < slack[b];
+        });
+        std::vector<Proto> sorted;
+        sorted.reserve(protos.size());
+        for (size_t i : ord) sorted.push_back(protos[i]);
+        protos.swap(sorted);
     }
     // bucket by (wave, class), stable
     std::vector<uint64_t> cnt((size_t)nwave * 3 + 1, 0);

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "pangulu_platform_0201001.h"
@@ -45,7 +46,7 @@ typedef calculate_type T;
     } while (0)
 #define CK_LAST() CK(cudaGetLastError())
 
-enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_NCLASS = 6 };
+enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_MEGA = 6, K_NCLASS = 7 };
 enum { K_GETRF_SMEM = 100, K_GETRF_DENSE = 101 };  // step kinds only; accounted under K_GETRF
 
 struct Options
@@ -57,6 +58,8 @@ struct Options
     long long getrf_mode = 0;  // 0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense
     long long tile_variant = 2; // 2 pipelined 512-thread tile kernel, 1 first-generation 256-thread kernel
     long long split_pairs = 1;  // split heavy destinations of thin waves over several CTAs
+    long long trace = 0;        // persistent executor: record per-task fetch/start/end timestamps (pangulu_sm100_plan_trace)
+    long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -76,8 +79,8 @@ struct Ctx
     cudaStream_t stream = nullptr;
     Options opt;
     std::vector<Slab> slabs;
-    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0};
-    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0};
+    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0};
+    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int max_smem_optin = 0;
     int sm_count = 0;
@@ -243,9 +246,12 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 if (d->brow_pos == d->bcol_pos && d->is_upper) return d->related_block;
                 return d;
             };
+            // first appearance of each destination in the caller's order = its priority
+            std::unordered_map<const void*, size_t> first_seen;
+            for (size_t k = 0; k < nrun; ++k) first_seen.emplace(key(k), k);
             std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-                const void *ka = key(a), *kb = key(b);
-                return ka != kb ? ka < kb : cls[a] < cls[b];
+                const size_t fa = first_seen[key(a)], fb = first_seen[key(b)];
+                return fa != fb ? fa < fb : cls[a] < cls[b];
             });
             std::vector<SsssmDest<T>> by_cls[2];
             const void* cur = nullptr;
@@ -315,10 +321,12 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             for (int c = 0; c < 2; ++c)
             {
                 if (by_cls[c].empty()) continue;
-                // heaviest destinations first: the grid is consumed in order, this trims the tail
-                std::stable_sort(by_cls[c].begin(), by_cls[c].end(), [](const SsssmDest<T>& x, const SsssmDest<T>& y) {
-                    return (x.pair_end - x.pair_begin) > (y.pair_end - y.pair_begin);
-                });
+                // per-wave launches: heaviest destinations first (the grid is consumed in order, this trims the tail);
+                // persistent executor: keep the caller's priority order
+                if (g.opt.executor != 1)
+                    std::stable_sort(by_cls[c].begin(), by_cls[c].end(), [](const SsssmDest<T>& x, const SsssmDest<T>& y) {
+                        return (x.pair_end - x.pair_begin) > (y.pair_end - y.pair_begin);
+                    });
                 Step st;
                 st.kind = c == 0 ? K_SSSSM_TILE : K_SSSSM_SPARSE;
                 st.off = P.dests.size();
@@ -346,7 +354,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 const size_t need = getrf_smem_bytes(nb, nl, nu);
                 // getrf_mode: 0 auto, 1 never stage in shared memory, 2 never promote to dense, 3 always dense (nb <= 256)
                 const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256;
-                if (!want_dense && need <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); }
+                if (!want_dense && need + 256 <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); }
                 else big.push_back(G);
                 if (eager_download)
                 {
@@ -661,7 +669,172 @@ struct pangulu_sm100_plan
     DevProgram D;
     std::vector<size_t> wave_step;  // wave w -> first step
     void* dev_buf;
+    // persistent executor
+    bool mega = false;
+    void* mega_buf = nullptr;
+    MegaParams<T> mp;
+    int* remaining_init = nullptr;
+    int* done_init = nullptr;
+    int* pending_init = nullptr;
+    size_t nids = 0;
+    std::vector<MegaTask> host_tasks;
 };
+
+namespace {
+
+// Translate the step list of a plan into the task list of the persistent executor (sm100_kernels.cuh,
+// mega_kernel): one task per (destination, 32-column tile) or (destination, 64-column group) of an SSSSM
+// step, one per GETRF / TSTRF / GESSM; synchronisation ids are assigned per distinct value array.
+void build_mega(pangulu_sm100_plan* pl)
+{
+    Program& P = pl->P;
+    const int nb = pl->nb;
+    std::unordered_map<const void*, int> ids;
+    auto id_of = [&](const void* p) {
+        auto it = ids.find(p);
+        if (it != ids.end()) return it->second;
+        const int id = (int)ids.size();
+        ids.emplace(p, id);
+        return id;
+    };
+    std::vector<MegaTask> tasks;
+    std::vector<int> dest_id(P.dests.size(), 0), remaining, pending;
+    std::vector<int2> pair_dep(P.pairs.size()), getrf_id(P.getrf.size()), panel_id(P.panel.size());
+    std::vector<char> produced;
+    auto touch = [&](int id) {
+        if ((size_t)id >= remaining.size()) { remaining.resize(id + 1, 0); produced.resize(id + 1, 0); pending.resize(id + 1, 0); }
+    };
+    for (size_t p = 0; p < P.pairs.size(); ++p)
+    {
+        pair_dep[p] = make_int2(id_of(P.pairs[p].a.val), id_of(P.pairs[p].b.val));
+        touch(pair_dep[p].x);
+        touch(pair_dep[p].y);
+    }
+    const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
+    const int sgroup = 64, sgroups = (nb + sgroup - 1) / sgroup;
+    for (const Step& st : P.steps)
+    {
+        switch (st.kind)
+        {
+        case K_SSSSM_TILE:
+        case K_SSSSM_SPARSE:
+            for (size_t d = st.off; d < st.off + st.count; ++d)
+            {
+                const int id = id_of(P.dests[d].c.val);
+                touch(id);
+                dest_id[d] = id;
+                if (st.kind == K_SSSSM_TILE)
+                {
+                    for (int t = 0; t < tiles; ++t) tasks.push_back({MEGA_TILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
+                    remaining[id] += tiles;
+                }
+                else
+                {
+                    for (int t = 0; t < sgroups; ++t) tasks.push_back({MEGA_SPARSE, (int)d, t * sgroup, sgroup});
+                    remaining[id] += sgroups;
+                }
+            }
+            break;
+        case K_GETRF:
+        case K_GETRF_SMEM:
+        case K_GETRF_DENSE:
+            for (size_t gi = st.off; gi < st.off + st.count; ++gi)
+            {
+                const int il = id_of(P.getrf[gi].lower.val), iu = id_of(P.getrf[gi].upper.val);
+                touch(il);
+                touch(iu);
+                getrf_id[gi] = make_int2(il, iu);
+                produced[il] = produced[iu] = 1;
+                tasks.push_back({st.kind == K_GETRF_SMEM ? MEGA_GETRF_SMEM : st.kind == K_GETRF_DENSE ? MEGA_GETRF_DENSE : MEGA_GETRF_GLOBAL, (int)gi, 0, 0});
+            }
+            break;
+        case K_TSTRF:
+            for (size_t ti = st.off; ti < st.off + st.count; ++ti)
+            {
+                const int ib = id_of(P.panel[ti].b.val), idg = id_of(P.panel[ti].diag.val);
+                touch(ib);
+                touch(idg);
+                panel_id[ti] = make_int2(ib, idg);
+                produced[ib] = 1;
+                for (int r0 = 0; r0 < nb; r0 += 64) { tasks.push_back({MEGA_PANEL, (int)ti, r0, 0}); pending[ib]++; }
+            }
+            break;
+        default: break;  // downloads are not part of a plan
+        }
+    }
+    const size_t nid = remaining.size();
+    std::vector<int> done_init(nid);
+    for (size_t i = 0; i < nid; ++i) done_init[i] = produced[i] ? 0 : 1;  // blocks no task of this plan produces are final already
+
+    const int nbp = (nb + 31) & ~31;
+    const size_t sz_tasks = vbytes(tasks), sz_pd = vbytes(pair_dep), sz_di = vbytes(dest_id), sz_gi = vbytes(getrf_id), sz_pi = vbytes(panel_id);
+    const size_t sz_ids = (nid * sizeof(int) + 255) & ~(size_t)255;
+    const size_t sz_scratch = ((size_t)g.sm_count * nbp * nbp * sizeof(T) + 255) & ~(size_t)255;
+    const size_t sz_trace = g.opt.trace ? ((tasks.size() * 3 * sizeof(unsigned long long) + 255) & ~(size_t)255) : 0;
+    const size_t total = sz_tasks + sz_pd + sz_di + sz_gi + sz_pi + 6 * sz_ids + 256 + sz_scratch + sz_trace;
+    char* d = nullptr;
+    CK(cudaMalloc((void**)&d, total));
+    pl->mega_buf = d;
+    char* q = d;
+    auto put = [&](const void* src, size_t bytes, size_t padded) {
+        char* at = q;
+        if (bytes) CK(cudaMemcpy(at, src, bytes, cudaMemcpyHostToDevice));
+        q += padded;
+        return at;
+    };
+    MegaParams<T>& mp = pl->mp;
+    mp.nb = nb;
+    mp.ntask = (int)tasks.size();
+    mp.tasks = (const MegaTask*)put(tasks.data(), tasks.size() * sizeof(MegaTask), sz_tasks);
+    mp.pair_dep = (const int2*)put(pair_dep.data(), pair_dep.size() * sizeof(int2), sz_pd);
+    mp.dest_id = (const int*)put(dest_id.data(), dest_id.size() * sizeof(int), sz_di);
+    mp.getrf_id = (const int2*)put(getrf_id.data(), getrf_id.size() * sizeof(int2), sz_gi);
+    mp.panel_id = (const int2*)put(panel_id.data(), panel_id.size() * sizeof(int2), sz_pi);
+    pl->remaining_init = (int*)put(remaining.data(), nid * sizeof(int), sz_ids);
+    pl->done_init = (int*)put(done_init.data(), nid * sizeof(int), sz_ids);
+    pl->pending_init = (int*)put(pending.data(), nid * sizeof(int), sz_ids);
+    mp.remaining = (int*)q; q += sz_ids;
+    mp.done = (int*)q; q += sz_ids;
+    mp.pending = (int*)q; q += sz_ids;
+    mp.counter = (int*)q; q += 256;
+    mp.scratch = (T*)q; q += sz_scratch;
+    mp.trace = sz_trace ? (unsigned long long*)q : nullptr;
+    pl->host_tasks = tasks;
+    mp.dests = pl->D.dests;
+    mp.pairs = pl->D.pairs;
+    mp.getrf = pl->D.getrf;
+    mp.panel = pl->D.panel;
+    pl->nids = nid;
+    pl->mega = true;
+}
+
+void run_mega(pangulu_sm100_plan* pl)
+{
+    MegaParams<T>& mp = pl->mp;
+    if (mp.ntask == 0) return;
+    CK(cudaMemcpyAsync(mp.remaining, pl->remaining_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaMemcpyAsync(mp.done, pl->done_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaMemcpyAsync(mp.pending, pl->pending_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
+    CK(cudaMemsetAsync(mp.counter, 0, sizeof(int), g.stream));
+    Timer tm(K_MEGA);
+    const size_t smem = (size_t)g.max_smem_optin - 64;
+    pl->mp.smem_bytes = smem;  // whole SM: the shared-memory GETRF variant sizes itself against this
+    const int grid = g.sm_count;
+    if (pl->nb <= 128)
+    {
+        CK(cudaFuncSetAttribute(mega_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mega_kernel<T, 128><<<grid, 512, smem, g.stream>>>(mp);
+    }
+    else
+    {
+        CK(cudaFuncSetAttribute(mega_kernel<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mega_kernel<T, 256><<<grid, 512, smem, g.stream>>>(mp);
+    }
+    CK_LAST();
+    g.launches[K_MEGA]++;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -802,6 +975,8 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "getrf_mode")) return &g.opt.getrf_mode;
     if (!strcmp(key, "tile_variant")) return &g.opt.tile_variant;
     if (!strcmp(key, "split_pairs")) return &g.opt.split_pairs;
+    if (!strcmp(key, "executor")) return &g.opt.executor;
+    if (!strcmp(key, "trace")) return &g.opt.trace;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)
@@ -861,6 +1036,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     pl->D.panel = (PanelTask<T>*)(d + b0);
     pl->D.dests = (SsssmDest<T>*)(d + b0 + b1);
     pl->D.pairs = (SsssmPair<T>*)(d + b0 + b1 + b2);
+    if (g.opt.executor == 1) build_mega(pl);
     // the host copies of the descriptor arrays are no longer needed; keep only the step list
     std::vector<GetrfTask<T>>().swap(P.getrf);
     std::vector<PanelTask<T>>().swap(P.panel);
@@ -878,12 +1054,37 @@ void pangulu_sm100_plan_execute_range(pangulu_sm100_plan* pl, pangulu_uint64_t w
     run_steps(pl->nb, pl->P, pl->D, pl->wave_step[w0], pl->wave_step[w1]);
 }
 
-void pangulu_sm100_plan_execute(pangulu_sm100_plan* pl) { pangulu_sm100_plan_execute_range(pl, 0, pl ? pl->wave_step.size() - 1 : 0); }
+void pangulu_sm100_plan_execute(pangulu_sm100_plan* pl)
+{
+    if (!pl) fatal(__FILE__, __LINE__, "null plan", nullptr);
+    if (pl->mega && g.opt.executor == 1) { run_mega(pl); return; }
+    pangulu_sm100_plan_execute_range(pl, 0, pl->wave_step.size() - 1);
+}
+
+// persistent executor trace: for task i, out[4i..4i+3] = {kind, fetch_ns, start_ns, end_ns}; returns the task count
+long long pangulu_sm100_plan_trace(pangulu_sm100_plan* pl, unsigned long long* out, long long cap)
+{
+    if (!pl || !pl->mega || !pl->mp.trace) return 0;
+    const long long n = pl->mp.ntask;
+    if (!out) return n;
+    std::vector<unsigned long long> tmp((size_t)n * 3);
+    CK(cudaMemcpy(tmp.data(), pl->mp.trace, tmp.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (long long i = 0; i < n && i < cap; ++i)
+    {
+        // kind in the low byte; for tile tasks the number of operand pairs above it
+        out[4 * i] = (unsigned long long)pl->host_tasks[i].kind | ((unsigned long long)(pl->host_tasks[i].kind == MEGA_TILE ? pl->host_tasks[i].c : 0) << 8);
+        out[4 * i + 1] = tmp[3 * i];
+        out[4 * i + 2] = tmp[3 * i + 1];
+        out[4 * i + 3] = tmp[3 * i + 2];
+    }
+    return n;
+}
 
 void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
 {
     if (!pl) return;
     if (pl->dev_buf) CK(cudaFree(pl->dev_buf));
+    if (pl->mega_buf) CK(cudaFree(pl->mega_buf));
     delete pl;
 }
 

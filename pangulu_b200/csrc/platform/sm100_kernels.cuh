@@ -1058,4 +1058,201 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
     ssssm_tile2_cta<T, TM>(smem_raw, nb, D, pairs, c0, false);
 }
 
+// ================================================================================================
+// Persistent executor ("megakernel"): the whole factorisation of one rank in ONE launch.
+//
+// PanguLU's scheduler is synchronisation-free on the host: per-block dependency counters, tasks fire when
+// their counter reaches zero (src/pangulu_numeric.c).  This kernel moves that idea onto the device.  One
+// resident CTA per SM pulls tasks from a list in topological order (atomic ticket), waits -- spinning on
+// per-block flags in global memory, acquire loads -- until the blocks it reads are final and (for
+// GETRF/TSTRF/GESSM) until every update of its destination has landed, runs the same CTA-level routines
+// the per-wave launches use, and publishes completion with a release.  No launch gaps, no wave barriers:
+// bulk SSSSM updates overlap the GETRF -> TSTRF/GESSM chain of the critical path.
+// Because updates of one destination now run concurrently, they are always combined with FP64 global
+// reductions.  A task only depends on tasks earlier in the list, and every fetched task is owned by a
+// running CTA, so the spin waits cannot deadlock.
+// ================================================================================================
+struct MegaTask { int kind, a, b, c; };
+enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5 };
+
+template <class T>
+struct MegaParams
+{
+    int nb, ntask;
+    const MegaTask* tasks;
+    const SsssmDest<T>* dests;
+    const SsssmPair<T>* pairs;
+    const int2* pair_dep;   // per pair: sync ids of A and B
+    const int* dest_id;     // per destination descriptor: sync id of the destination
+    const GetrfTask<T>* getrf;
+    const int2* getrf_id;   // sync ids of the lower and the upper half
+    const PanelTask<T>* panel;
+    const int2* panel_id;   // x: sync id of the panel block, y: sync id of the diagonal half it is solved against
+    int* remaining;         // per sync id: SSSSM sub-tasks still to land on the block
+    int* done;              // per sync id: 1 once the block is final
+    int* pending;           // per sync id: TSTRF/GESSM sub-tasks (16 rows/columns each) still running
+    int* counter;           // ticket
+    T* scratch;             // dense GETRF tile per CTA
+    size_t smem_bytes;      // dynamic shared memory the kernel was launched with
+    unsigned long long* trace;  // optional: per task {fetch, start, end} in ns (globaltimer), else null
+};
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void spin_until_set(const int* flag)
+{
+    unsigned ns = 20;
+    while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+}
+__device__ __forceinline__ void spin_until_zero(const int* cnt)
+{
+    unsigned ns = 20;
+    while (ld_acquire(cnt) != 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+}
+
+// cooperative global -> shared copy of `bytes` bytes (both 16-byte aligned at the start), 128-bit accesses, 4 in flight
+__device__ __forceinline__ void stage_copy(void* dst, const void* src, size_t bytes, int tid, int nthreads)
+{
+    const size_t nvec = bytes / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    size_t i = tid;
+    for (; i + 3 * (size_t)nthreads < nvec; i += 4 * (size_t)nthreads)
+    {
+        const uint4 a = s4[i], b = s4[i + nthreads], c = s4[i + 2 * (size_t)nthreads], d = s4[i + 3 * (size_t)nthreads];
+        d4[i] = a; d4[i + nthreads] = b; d4[i + 2 * (size_t)nthreads] = c; d4[i + 3 * (size_t)nthreads] = d;
+    }
+    for (; i < nvec; i += nthreads) d4[i] = s4[i];
+    const unsigned char* sb = reinterpret_cast<const unsigned char*>(src);
+    unsigned char* db = reinterpret_cast<unsigned char*>(dst);
+    for (size_t k = nvec * 16 + tid; k < bytes; k += nthreads) db[k] = sb[k];
+}
+
+template <class T, int TM>
+__global__ void __launch_bounds__(512, 1)
+mega_kernel(const MegaParams<T> P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ int s_ticket;
+    const int tid = threadIdx.x, warp = tid / PSM_WARP;
+    const int nb = P.nb;
+    for (;;)
+    {
+        if (tid == 0) s_ticket = atomicAdd(P.counter, 1);
+        __syncthreads();
+        const int t = s_ticket;
+        if (t >= P.ntask) break;
+        const MegaTask mt = P.tasks[t];
+        if (P.trace && tid == 0) P.trace[3 * (size_t)t] = global_ns();
+        switch (mt.kind)
+        {
+        case MEGA_TILE:
+        case MEGA_SPARSE:
+        {
+            const SsssmDest<T> D = P.dests[mt.a];
+            if (tid == 0)
+                for (u32 p = D.pair_begin; p < D.pair_end; ++p)
+                {
+                    const int2 dep = P.pair_dep[p];
+                    spin_until_set(P.done + dep.x);
+                    spin_until_set(P.done + dep.y);
+                }
+            __syncthreads();
+            if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (mt.kind == MEGA_TILE)
+                ssssm_tile2_cta<T, TM>(smem_raw, nb, D, P.pairs, mt.b * PSM_TILE_N, true);
+            else
+            {
+                T* acc = reinterpret_cast<T*>(smem_raw) + (size_t)warp * nb;
+                for (int j = mt.b + warp; j < mt.b + mt.c && j < nb; j += 16) ssssm_sparse_column<T>(nb, D, P.pairs, j, acc, true);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicSub(P.remaining + P.dest_id[mt.a], 1);
+            break;
+        }
+        case MEGA_GETRF_SMEM:
+        case MEGA_GETRF_DENSE:
+        case MEGA_GETRF_GLOBAL:
+        {
+            const GetrfTask<T> G = P.getrf[mt.a];
+            const int2 id = P.getrf_id[mt.a];
+            if (tid == 0) spin_until_zero(P.remaining + id.x);
+            __syncthreads();
+            if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (mt.kind == MEGA_GETRF_SMEM)
+                getrf_smem_cta<T, 512>(smem_raw, nb, G);
+            else if (mt.kind == MEGA_GETRF_DENSE)
+            {
+                const int nbp = (nb + 31) & ~31;
+                getrf_dense_cta<T, 512>(smem_raw, nb, G, P.scratch + (size_t)blockIdx.x * nbp * nbp);
+            }
+            else
+            {
+                T* buf = reinterpret_cast<T*>(smem_raw);
+                for (int i = tid; i < 4 * nb; i += 512) buf[i] = zero<T>();
+                __syncthreads();
+                getrf_body<T, 512>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf);
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) { st_release(P.done + id.x, 1); st_release(P.done + id.y, 1); }
+            break;
+        }
+        case MEGA_PANEL:
+        {
+            const PanelTask<T> Q = P.panel[mt.a];
+            const int2 id = P.panel_id[mt.a];
+            if (tid == 0) { spin_until_set(P.done + id.y); spin_until_zero(P.remaining + id.x); }
+            __syncthreads();
+            if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            // one task = 64 consecutive rows/columns of the block (four per warp); the diagonal half they are solved
+            // against is staged in shared memory when it fits.  The last sub-task of a block to finish publishes it.
+            T* x = reinterpret_cast<T*>(smem_raw) + (size_t)warp * nb;
+            PanelTask<T> Q2 = Q;
+            {
+                unsigned char* stage = smem_raw + (size_t)16 * nb * sizeof(T);
+                const size_t budget = P.smem_bytes - (size_t)16 * nb * sizeof(T);
+                const u32 nd = Q.diag.ptr[nb];
+                const size_t need = (size_t)nd * (sizeof(T) + 2) + 4 * (size_t)(nb + 1) + 64;
+                if (need <= budget)
+                {
+                    T* sval = reinterpret_cast<T*>(stage);
+                    u32* sptr = reinterpret_cast<u32*>(stage + (((size_t)nd * sizeof(T) + 15) & ~(size_t)15));
+                    u16* sidx = reinterpret_cast<u16*>(reinterpret_cast<unsigned char*>(sptr) + ((4 * (size_t)(nb + 1) + 15) & ~(size_t)15));
+                    if ((reinterpret_cast<size_t>(Q.diag.val) & 15) == 0 && (reinterpret_cast<size_t>(Q.diag.idx) & 15) == 0)
+                    {
+                        stage_copy(sval, Q.diag.val, (size_t)nd * sizeof(T), tid, 512);
+                        stage_copy(sidx, Q.diag.idx, (size_t)nd * 2, tid, 512);
+                    }
+                    else
+                        for (u32 i = tid; i < nd; i += 512) { sval[i] = Q.diag.val[i]; sidx[i] = Q.diag.idx[i]; }
+                    for (int i = tid; i <= nb; i += 512) sptr[i] = i == 0 ? 0u : Q.diag.ptr[i];
+                    Q2.diag.val = sval; Q2.diag.ptr = sptr; Q2.diag.idx = sidx;
+                }
+                __syncthreads();
+            }
+            for (int rc = mt.b + warp; rc < mt.b + 64 && rc < nb; rc += 16) panel_solve_line<T>(nb, Q2, rc, x);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0 && atomicSub(P.pending + id.x, 1) == 1) { __threadfence(); st_release(P.done + id.x, 1); }
+            break;
+        }
+        }
+        __syncthreads();
+        if (P.trace && tid == 0) P.trace[3 * (size_t)t + 2] = global_ns();
+    }
+}
+
 }  // namespace psm
