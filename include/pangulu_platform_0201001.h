@@ -101,9 +101,13 @@ void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t *s, calculate_ty
  *                     host slot->value, as pangulu_cuda_download_block does (…0201000.cu:196-201,639-640,680,714)
  *                     -- but asynchronously; complete after PSM(synchronize).  0: the caller promises to
  *                     call pangulu_sm100_download_blocks() itself (one bulk copy at the end of gstrf).
- *   "dense_threshold" per-mille block density (nnz*1000/nb^2) from which SSSSM runs on the dense
- *                     FP64/FP32 tensor-core tile path (default 250)
+ *   "dense_threshold" per-mille operand density sqrt(nnzA*nnzB)/nb^2 from which an SSSSM update runs on the dense
+ *                     FP64 tensor-core (DMMA) / FP32 FMA tile path (default 120)
  *   "ssssm_mode"      0 auto, 1 force sparse path, 2 force tile path
+ *   "getrf_mode"      0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense-promoted (nb <= 256)
+ *   "executor"        plans only: 1 (default) persistent megakernel -- one launch per factorisation, device-side
+ *                     dependency flags; 0 one launch per kernel class per wave
+ *   "split_pairs", "tile_variant", "profile", "trace"   tuning / instrumentation, see DESIGN.md
  * returns 0, or -1 for an unknown key. */
 int pangulu_sm100_set_option(const char *key, long long value);
 long long pangulu_sm100_get_option(const char *key);

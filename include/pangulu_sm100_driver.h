@@ -51,8 +51,9 @@ void pangulu_finalize(void **pangulu_handle);
  *   "rank", "nproc"   position in the p x q rank grid (one rank per GPU)
  *   "ordering"        0 natural (input already permuted), 1 METIS_NodeND, -1 (default) METIS when built in
  *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan
- *   "schedule"        1 (default) eager: every SSSSM update runs in the first wave after both of its operands are
- *                     final; 0 lazy: all updates of a destination run in the wave that finalises it
+ *   "schedule"        wave of an SSSSM update: 0 lazy (the wave that finalises its destination), 1 eager (first wave
+ *                     after both operands are final), 2 (default) windowed: max(eager, destination's wave - "lookahead")
+ *   "lookahead"       window of policy 2 in waves (default 6)
  *   "verbose"         1 prints the reference's info lines
  *   "host_only"       1 builds ordering/symbolic/blocks/schedule in host memory only (CPU-side tests of the
  *                     host logic); pangulu_gstrf on such a handle is a fatal error -- there is no CPU path

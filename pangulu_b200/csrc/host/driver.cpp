@@ -34,7 +34,7 @@ struct DriverConfig
     long long mode = 0;
     long long verbose = 0;
     long long host_only = 0;
-    long long schedule = 1;
+    long long schedule = 2;
     long long lookahead = 6;
 };
 DriverConfig g_cfg;

@@ -122,7 +122,7 @@ struct Schedule
     std::vector<int32_t> depth_offdiag; // per global off-diagonal block
     std::vector<int32_t> depth_diag;    // per block row
     uint64_t n_getrf = 0, n_tstrf = 0, n_gessm = 0, n_ssssm = 0;
-    int policy = 1;                     // 0 lazy (updates in the destination's wave), 1 eager (as soon as operands are final), 2 windowed
+    int policy = 2;                     // 0 lazy (updates in the destination's wave), 1 eager (as soon as operands are final), 2 windowed
     int lookahead = 6;                  // policy 2: waves before the destination's finalisation at which slack updates run
 };
 void build_schedule(BlockStore& B, Schedule& S);

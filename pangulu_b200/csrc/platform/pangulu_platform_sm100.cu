@@ -52,7 +52,7 @@ enum { K_GETRF_SMEM = 100, K_GETRF_DENSE = 101 };  // step kinds only; accounted
 struct Options
 {
     long long eager_download = 1;
-    long long dense_threshold = 250;
+    long long dense_threshold = 120;
     long long ssssm_mode = 0;
     long long profile = 0;
     long long getrf_mode = 0;  // 0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense
@@ -508,7 +508,7 @@ template <int TM> void launch_ssssm_tile2_t(int nb, const SsssmDest<T>* d, const
 {
     const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
     const size_t a = (size_t)2 * PSM_TILE_K * (TM + 4 + PSM_TILE_N + 4), c = (size_t)PSM_TILE_N * (TM + 4);
-    const size_t smem = std::max(a, c) * sizeof(T);
+    const size_t smem = std::max(a, c) * sizeof(T) + 4 * (size_t)(TM + 4) + 4 * (size_t)PSM_TILE_N * (TM / PSM_TILE_K + 1) + 64;
     set_smem(ssssm_tile2_kernel<T, TM>, smem);
     ssssm_tile2_kernel<T, TM><<<(unsigned)(ndest * tiles), 512, smem, g.stream>>>(nb, d, p, tiles);
     CK_LAST();

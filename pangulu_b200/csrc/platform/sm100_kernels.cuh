@@ -866,125 +866,137 @@ __device__ __forceinline__ void ssssm_tile2_cta(unsigned char* smem_raw, int nb,
     for (int i = tid; i < 2 * KC * (LDA + LDB); i += 512) sm[i] = zero<T>();
 
     // ---- fetch stage state -----------------------------------------------------------------------------
+    // Per operand pair a short prologue puts A's column pointers and, for each of the 32 B columns, the offset of
+    // the first entry of every 16-row chunk into shared memory.  After that a chunk's loads need no dependent
+    // global reads: they are issued right after the barrier and land while the tensor phase runs.
+    constexpr size_t kBig = (2 * KC * (LDA + LDB) > TN * LDA) ? 2 * KC * (LDA + LDB) : TN * LDA;
+    u32* sAptr = reinterpret_cast<u32*>(sm + kBig);          // [TM + 1]
+    int* sBoff = reinterpret_cast<int*>(sAptr + (TM + 4));    // [TN][KCH + 1], KCH = TM / KC chunks
+    constexpr int KCH = TM / KC;
     const int b_jj = tid / 16, b_l = tid % 16;
     const int b_col = c0 + b_jj;
-    const unsigned grp_shift = (lane / 16) * 16;
-    u32 p = D.pair_begin;
     int k0 = 0;
     BlkRO<T> A, B;
-    u32 cur = 0, bend = 0;
+    u32 bbeg = 0;
     u16 aidx[AR];
     T aval[AR];
-    int brow = -1;
+    int bidx = -1;
     T bval = zero<T>();
-    auto load_pair = [&]() {
-        A = pairs[p].a;
-        B = pairs[p].b;
-        cur = 0;
-        bend = 0;
-        if (b_jj < ncol) { cur = col_begin(B.ptr, b_col); bend = B.ptr[b_col + 1]; }
-    };
-    // advance to the next chunk whose A columns are not all empty and pull its entries into registers
+    // next chunk of the CURRENT pair whose A columns are not all empty -> registers; false at the end of the pair
     auto fetch = [&]() -> bool {
-        for (;;)
+        for (; k0 < nb; k0 += KC)
         {
-            if (k0 >= nb)
-            {
-                ++p;
-                k0 = 0;
-                if (p >= D.pair_end) return false;
-                load_pair();
-            }
             const int kc = min(KC, nb - k0);
-            const bool a_has = A.ptr[k0 + kc] > col_begin(A.ptr, k0);
-            {
-                const u32 e = cur + b_l;
-                bool in = false;
-                int r = 0;
-                if (e < bend) { r = B.idx[e]; in = r < k0 + kc; }
-                brow = -1;
-                if (a_has && in) { bval = B.val[e]; brow = r - k0; }
-                const unsigned m = __ballot_sync(PSM_FULL, in);
-                cur += __popc((m >> grp_shift) & 0xffffu);
-            }
-            if (a_has)
-            {
-                u32 a0 = 0, a1 = 0;
-                if (warp < kc) { a0 = col_begin(A.ptr, k0 + warp); a1 = A.ptr[k0 + warp + 1]; }
-#pragma unroll
-                for (int i = 0; i < AR; ++i)
-                {
-                    const u32 e = a0 + lane + 32 * i;
-                    aidx[i] = 0xffff;
-                    if (e < a1) { aidx[i] = A.idx[e]; aval[i] = A.val[e]; }
-                }
-                k0 += KC;
-                return true;
-            }
-            k0 += KC;
-        }
-    };
-
-    bool more = false;
-    if (p < D.pair_end) { load_pair(); more = fetch(); }
-    __syncthreads();
-    int it = 0;
-    while (more)
-    {
-        const int buf = it & 1;
-        T* As = As0 + buf * KC * LDA;
-        T* Bs = Bs0 + buf * KC * LDB;
-        {
-            T* Ak = As + warp * LDA;
+            if (sAptr[k0 + kc] == sAptr[k0]) continue;
+            const int ch = k0 / KC;
+            const int o0 = sBoff[b_jj * (KCH + 1) + ch], o1 = sBoff[b_jj * (KCH + 1) + ch + 1];
+            bidx = -1;
+            if (o0 + b_l < o1) { bidx = B.idx[bbeg + o0 + b_l]; bval = B.val[bbeg + o0 + b_l]; }
+            u32 a0 = 0, a1 = 0;
+            if (warp < kc) { a0 = sAptr[k0 + warp]; a1 = sAptr[k0 + warp + 1]; }
 #pragma unroll
             for (int i = 0; i < AR; ++i)
-                if (aidx[i] != 0xffff) Ak[aidx[i]] = aval[i];
-            if (brow >= 0) Bs[brow * LDB + b_jj] = bval;
+            {
+                const u32 e = a0 + lane + 32 * i;
+                aidx[i] = 0xffff;
+                if (e < a1) { aidx[i] = A.idx[e]; aval[i] = A.val[e]; }
+            }
+            k0 += KC;
+            return true;
+        }
+        return false;
+    };
+
+    int it = 0;
+    for (u32 p = D.pair_begin; p < D.pair_end; ++p)
+    {
+        A = pairs[p].a;
+        B = pairs[p].b;
+        // ---- pair prologue
+        __syncthreads();  // previous pair's chunks are done with sAptr / sBoff
+        for (int i = tid; i <= nb; i += 512) sAptr[i] = i == 0 ? 0u : A.ptr[i];
+        for (int i = tid; i < TN * (KCH + 1); i += 512) sBoff[i] = 0;
+        u32 bend = 0;
+        bbeg = 0;
+        if (b_jj < ncol) { bbeg = col_begin(B.ptr, b_col); bend = B.ptr[b_col + 1]; }
+        u16 rr[KCH];
+#pragma unroll
+        for (int i = 0; i < KCH; ++i)
+        {
+            const u32 e = bbeg + b_l + 16 * i;
+            rr[i] = 0xffff;
+            if (e < bend) rr[i] = B.idx[e];
         }
         __syncthreads();
-        more = fetch();  // loads of the next chunk stay in flight during the tensor phase below
+#pragma unroll
+        for (int i = 0; i < KCH; ++i)
+            if (rr[i] != 0xffff) atomicAdd(&sBoff[b_jj * (KCH + 1) + (rr[i] / KC) + 1], 1);
+        __syncthreads();
+        if (b_l == 0)
         {
-            T* Ao = As0 + (buf ^ 1) * KC * LDA;
-            T* Bo = Bs0 + (buf ^ 1) * KC * LDB;
-            for (int i = tid; i < KC * LDA; i += 512) Ao[i] = zero<T>();
-            for (int i = tid; i < KC * LDB; i += 512) Bo[i] = zero<T>();
+            int run = 0;
+            for (int c = 1; c <= KCH; ++c) { run += sBoff[b_jj * (KCH + 1) + c]; sBoff[b_jj * (KCH + 1) + c] = run; }
         }
-        if constexpr (kDouble)
+        __syncthreads();
+        k0 = 0;
+        bool more = fetch();
+        while (more)
         {
-            const int lr = lane / 4, lk = lane % 4;
-#pragma unroll
-            for (int k4 = 0; k4 < KC; k4 += 4)
+            const int buf = it & 1;
+            T* As = As0 + buf * KC * LDA;
+            T* Bs = Bs0 + buf * KC * LDB;
             {
-                double a[4], b[NT];
+                T* Ak = As + warp * LDA;
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt) a[mt] = As[(k4 + lk) * LDA + m_base + mt * 8 + lr];
-#pragma unroll
-                for (int nt = 0; nt < NT; ++nt) b[nt] = Bs[(k4 + lk) * LDB + n_base + nt * 8 + lr];
-#pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) dmma884(acc[(mt * NT + nt) * 2], acc[(mt * NT + nt) * 2 + 1], a[mt], b[nt]);
+                for (int i = 0; i < AR; ++i)
+                    if (aidx[i] != 0xffff) Ak[aidx[i]] = aval[i];
+                if (bidx >= 0) Bs[(bidx % KC) * LDB + b_jj] = bval;
             }
-        }
-        else
-        {
-            // FMA register tile: thread (tx, ty) owns rows tx + 32 i (i < TM/32) and columns 2 ty, 2 ty + 1
-            const int tx = tid % 32, ty = tid / 32;
-#pragma unroll 4
-            for (int kk = 0; kk < KC; ++kk)
+            __syncthreads();
+            more = fetch();  // loads of the next chunk stay in flight during the tensor phase below
             {
-                const T b0 = Bs[kk * LDB + ty * 2], b1 = Bs[kk * LDB + ty * 2 + 1];
+                T* Ao = As0 + (buf ^ 1) * KC * LDA;
+                T* Bo = Bs0 + (buf ^ 1) * KC * LDB;
+                for (int i = tid; i < KC * LDA; i += 512) Ao[i] = zero<T>();
+                for (int i = tid; i < KC * LDB; i += 512) Bo[i] = zero<T>();
+            }
+            if constexpr (kDouble)
+            {
+                const int lr = lane / 4, lk = lane % 4;
 #pragma unroll
-                for (int i = 0; i < TM / 32; ++i)
+                for (int k4 = 0; k4 < KC; k4 += 4)
                 {
-                    const T av = As[kk * LDA + tx + 32 * i];
-                    fma_acc(acc[i * 2], av, b0);
-                    fma_acc(acc[i * 2 + 1], av, b1);
+                    double a[4], b[NT];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt) a[mt] = As[(k4 + lk) * LDA + m_base + mt * 8 + lr];
+#pragma unroll
+                    for (int nt = 0; nt < NT; ++nt) b[nt] = Bs[(k4 + lk) * LDB + n_base + nt * 8 + lr];
+#pragma unroll
+                    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) dmma884(acc[(mt * NT + nt) * 2], acc[(mt * NT + nt) * 2 + 1], a[mt], b[nt]);
                 }
             }
+            else
+            {
+                // FMA register tile: thread (tx, ty) owns rows tx + 32 i (i < TM/32) and columns 2 ty, 2 ty + 1
+                const int tx = tid % 32, ty = tid / 32;
+#pragma unroll 4
+                for (int kk = 0; kk < KC; ++kk)
+                {
+                    const T b0 = Bs[kk * LDB + ty * 2], b1 = Bs[kk * LDB + ty * 2 + 1];
+#pragma unroll
+                    for (int i = 0; i < TM / 32; ++i)
+                    {
+                        const T av = As[kk * LDA + tx + 32 * i];
+                        fma_acc(acc[i * 2], av, b0);
+                        fma_acc(acc[i * 2 + 1], av, b1);
+                    }
+                }
+            }
+            __syncthreads();
+            ++it;
         }
-        __syncthreads();
-        ++it;
     }
 
     // epilogue: accumulator -> shared memory (column major [TN][LDA]) -> destination pattern

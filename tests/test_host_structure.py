@@ -66,7 +66,7 @@ def test_structure_matches_live_reference(make, nb):
         s.finalize()
 
 
-@pytest.mark.parametrize("policy", [0, 1], ids=["lazy", "eager"])
+@pytest.mark.parametrize("policy", [0, 1, 2], ids=["lazy", "eager", "windowed"])
 def test_schedule_respects_dependencies(policy):
     """Every task of the static schedule runs in a later wave than the tasks that produce its operands, and no
     update of a destination runs after the wave that finalises it (lazy policy: exactly in that wave)."""
@@ -93,11 +93,13 @@ def test_schedule_respects_dependencies(policy):
                 assert final[diag_lower] < w
             if t["kernel_id"] == _lib.TASK_SSSSM:
                 assert final[int(t["op1"])] < w and final[int(t["op2"])] < w
+                ready = 1 + max(final[int(t["op1"])], final[int(t["op2"])])
                 if policy == 0:
                     assert final[int(t["opdst"])] == w  # applied in the wave that finalises the destination
+                elif policy == 1:
+                    assert w <= final[int(t["opdst"])] and w == ready  # as early as possible
                 else:
-                    assert w <= final[int(t["opdst"])]
-                    assert w == 1 + max(final[int(t["op1"])], final[int(t["op2"])])  # as early as possible
+                    assert w == max(ready, final[int(t["opdst"])] - 6)  # windowed, default lookahead
                 n_upd += 1
         assert n_upd == int(s.info("n_ssssm")) and n_upd > 0
         # within a wave: SSSSM first, then GETRF, then TSTRF/GESSM
