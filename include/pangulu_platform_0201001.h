@@ -134,6 +134,29 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan *plan);
  * (4 u64 per task) of the last execution; returns the number of tasks (call with out = NULL to size the buffer) */
 long long pangulu_sm100_plan_trace(pangulu_sm100_plan *plan, unsigned long long *out, long long cap);
 
+/* Multi-GPU wiring of a persistent plan (one rank per GPU).  A block finalised by its owner is written by the
+ * producing kernel itself into the mirror copy every consumer rank keeps (peer-mapped pointers over NVLink /
+ * NVSwitch, obtained with CUDA IPC), followed by a system-scope release of the consumer's "done" flag -- this
+ * replaces pangulu_cm_isend_block / pangulu_cm_recv_block (src/pangulu_communication.c:1902-1944, 1786-1900):
+ * no host staging, no MPI, no probe loop.
+ *   sync_base / flag_offset   where the plan keeps the done flag of the block whose device value array is d_value
+ *                             (the allocation is exported with pangulu_sm100_ipc_export)
+ *   expect_remote             the block is produced by a peer: its flag starts cleared
+ *   add_push                  after finalising the local block d_value_local, copy its values to peer_value and
+ *                             raise *peer_flag (both pointers are peer-mapped)
+ *   commit                    upload the push lists;  reset / launch = the two halves of plan_execute (all ranks
+ *                             must have reset before any rank launches: put a host barrier in between) */
+void *pangulu_sm100_plan_sync_base(pangulu_sm100_plan *plan, size_t *bytes);
+long long pangulu_sm100_plan_flag_offset(pangulu_sm100_plan *plan, const void *d_value);
+void pangulu_sm100_plan_expect_remote(pangulu_sm100_plan *plan, const void *d_value);
+void pangulu_sm100_plan_add_push(pangulu_sm100_plan *plan, const void *d_value_local, void *peer_value, void *peer_flag);
+void pangulu_sm100_plan_commit(pangulu_sm100_plan *plan);
+void pangulu_sm100_plan_reset(pangulu_sm100_plan *plan);
+void pangulu_sm100_plan_launch(pangulu_sm100_plan *plan);
+/* CUDA IPC: 64-byte handle of a device allocation of this module / map a peer's allocation into this process */
+int pangulu_sm100_ipc_export(void *devptr, void *handle64);
+int pangulu_sm100_ipc_open(const void *handle64, void **devptr);
+
 /* Instrumentation (bench.py): kernels launched / device time per kernel class since the last reset.
  * cls: 0 getrf, 1 tstrf, 2 gessm, 3 ssssm-sparse, 4 ssssm-tile, 5 copy/aux.  Timing is off unless
  * option "profile" is 1 (it brackets every launch with CUDA events on the module's stream). */

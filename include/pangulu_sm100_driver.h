@@ -75,6 +75,17 @@ void pangulu_sm100_driver_reset_values(void *handle, int also_device);
 /* resident mode: enqueue the whole factorisation on the module's stream (pangulu_sm100_stream()) without
  * synchronising; <id>_synchronize() or a stream event completes it */
 void pangulu_sm100_driver_gstrf_enqueue(void *handle);
+/* Multi-GPU (one rank per GPU, 2D block-cyclic ownership as src/pangulu_common.h:135).  Every rank builds its own
+ * handle with "rank"/"nproc" set, then the ranks exchange ipc_handles + mirror_table (any host channel, e.g.
+ * torch.distributed.all_gather_object), call connect_peer once per peer and commit.  pangulu_gstrf then needs a
+ * host barrier (set_barrier).  Finished blocks travel GPU-to-GPU inside the factorisation kernel. */
+void pangulu_sm100_driver_set_barrier(void (*fn)(void));
+void pangulu_sm100_driver_ipc_handles(void *handle, unsigned char *out128);
+long long pangulu_sm100_driver_mirror_table(void *handle, long long *out, long long cap);
+long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *handles128, const long long *table, long long n);
+void pangulu_sm100_driver_commit(void *handle);
+void pangulu_sm100_driver_gstrf_reset(void *handle);
+void pangulu_sm100_driver_gstrf_launch(void *handle);
 /* task trace of the last resident gstrf (see pangulu_sm100_plan_trace) */
 long long pangulu_sm100_driver_trace(void *handle, unsigned long long *out, long long cap);
 /* device -> host copy of the owned factors (resident mode) */

@@ -30,6 +30,9 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_plan_create", "pangulu_sm100_plan_execute", "pangulu_sm100_plan_execute_range",
     "pangulu_sm100_plan_destroy", "pangulu_sm100_stats_reset", "pangulu_sm100_stats_launches",
     "pangulu_sm100_stats_ms", "pangulu_sm100_stream", "pangulu_sm100_version", "pangulu_sm100_plan_trace",
+    "pangulu_sm100_plan_sync_base", "pangulu_sm100_plan_flag_offset", "pangulu_sm100_plan_expect_remote",
+    "pangulu_sm100_plan_add_push", "pangulu_sm100_plan_commit", "pangulu_sm100_plan_reset", "pangulu_sm100_plan_launch",
+    "pangulu_sm100_ipc_export", "pangulu_sm100_ipc_open",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [
@@ -37,7 +40,9 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_config", "pangulu_sm100_driver_info", "pangulu_sm100_driver_slot",
     "pangulu_sm100_driver_perm", "pangulu_sm100_driver_tasks", "pangulu_sm100_driver_reset_values",
     "pangulu_sm100_driver_download", "pangulu_sm100_driver_factor_check", "pangulu_sm100_driver_gstrf_enqueue",
-    "pangulu_sm100_driver_trace",
+    "pangulu_sm100_driver_trace", "pangulu_sm100_driver_set_barrier", "pangulu_sm100_driver_ipc_handles",
+    "pangulu_sm100_driver_mirror_table", "pangulu_sm100_driver_connect_peer", "pangulu_sm100_driver_commit",
+    "pangulu_sm100_driver_gstrf_reset", "pangulu_sm100_driver_gstrf_launch",
 ]
 
 
@@ -153,6 +158,15 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_driver_reset_values.argtypes = [vp, C.c_int]
     L.pangulu_sm100_driver_download.argtypes = [vp]
     L.pangulu_sm100_driver_gstrf_enqueue.argtypes = [vp]
+    L.pangulu_sm100_driver_set_barrier.argtypes = [vp]
+    L.pangulu_sm100_driver_ipc_handles.argtypes = [vp, vp]
+    L.pangulu_sm100_driver_mirror_table.argtypes = [vp, vp, C.c_longlong]
+    L.pangulu_sm100_driver_mirror_table.restype = C.c_longlong
+    L.pangulu_sm100_driver_connect_peer.argtypes = [vp, vp, vp, C.c_longlong]
+    L.pangulu_sm100_driver_connect_peer.restype = C.c_longlong
+    L.pangulu_sm100_driver_commit.argtypes = [vp]
+    L.pangulu_sm100_driver_gstrf_reset.argtypes = [vp]
+    L.pangulu_sm100_driver_gstrf_launch.argtypes = [vp]
     L.pangulu_sm100_driver_trace.argtypes = [vp, vp, C.c_longlong]
     L.pangulu_sm100_driver_trace.restype = C.c_longlong
     L.pangulu_sm100_plan_trace.argtypes = [vp, vp, C.c_longlong]

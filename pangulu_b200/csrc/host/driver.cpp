@@ -38,6 +38,7 @@ struct DriverConfig
     long long lookahead = 6;
 };
 DriverConfig g_cfg;
+void (*g_barrier)(void) = nullptr;  // host barrier across ranks (multi-GPU), installed by the launcher
 
 struct Handle
 {
@@ -183,6 +184,7 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         exit(EXIT_FAILURE);
     }
     h->mode = (int)g_cfg.mode;  // the mode may be switched between calls (bench.py times both on one handle)
+    if (g_cfg.nproc > 1) h->mode = 1;
     if (h->mode == 1 && !h->plan)
     {
         const double tp = wall_seconds();
@@ -191,7 +193,23 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         h->times["plan"] = wall_seconds() - tp;
     }
     const double t0 = wall_seconds();
-    if (h->mode == 1 && g_cfg.nproc == 1)
+    if (g_cfg.nproc > 1)
+    {
+        // one rank per GPU: the plan must have been wired to the peers (pangulu_sm100_driver_connect_peer/commit);
+        // every rank clears its flags, all ranks meet, then the persistent kernels run and push blocks to each other
+        if (!g_barrier || !h->plan)
+        {
+            fprintf(stderr, "[PanguLU ERROR] multi-rank gstrf needs a wired plan and a barrier (pangulu_sm100_driver_set_barrier)\n");
+            exit(EXIT_FAILURE);
+        }
+        pangulu_sm100_plan_reset(h->plan);
+        PSM(synchronize)();
+        g_barrier();
+        pangulu_sm100_plan_launch(h->plan);
+        PSM(synchronize)();
+        g_barrier();
+    }
+    else if (h->mode == 1)
     {
         pangulu_sm100_plan_execute(h->plan);
         PSM(synchronize)();
@@ -353,6 +371,109 @@ void pangulu_sm100_driver_gstrf_enqueue(void* handle)
     pangulu_sm100_plan_execute(h->plan);
     h->factored = true;
 }
+
+// ---- multi-GPU wiring (one rank per GPU; see pangulu_sm100_plan_* in the platform header) ----------------------
+void pangulu_sm100_driver_set_barrier(void (*fn)(void)) { g_barrier = fn; }
+
+static void ensure_plan(Handle* h)
+{
+    if (!h->plan)
+        h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
+                                            h->sched.tasks.data());
+}
+
+// 128 bytes: CUDA IPC handles of this rank's block buffer and of its plan's synchronisation buffer
+void pangulu_sm100_driver_ipc_handles(void* handle, unsigned char* out128)
+{
+    Handle* h = (Handle*)handle;
+    ensure_plan(h);
+    pangulu_sm100_ipc_export(h->B.d_buf, out128);
+    size_t bytes = 0;
+    pangulu_sm100_ipc_export(pangulu_sm100_plan_sync_base(h->plan, &bytes), out128 + 64);
+}
+
+// One row of 5 int64 per remote block this rank mirrors AND reads: {brow, bcol, kind (0 off-diagonal, 1 lower half,
+// 2 upper half of a diagonal block), byte offset of its value array in the block buffer, byte offset of its done flag
+// in the plan's synchronisation buffer}.  Also tells the plan that these blocks arrive from a peer.
+long long pangulu_sm100_driver_mirror_table(void* handle, long long* out, long long cap)
+{
+    Handle* h = (Handle*)handle;
+    BlockStore& B = h->B;
+    long long n = 0;
+    if (!B.host_only) ensure_plan(h);
+    for (const pangulu_storage_slot_t& s : B.slots)
+    {
+        if (s.bin_id == 0) continue;
+        long long flag = -1;
+        if (!B.host_only)
+        {
+            flag = pangulu_sm100_plan_flag_offset(h->plan, s.d_value);
+            if (flag < 0) continue;  // mirrored but never read by a task of this rank
+            pangulu_sm100_plan_expect_remote(h->plan, s.d_value);
+        }
+        if (out && n < cap)
+        {
+            long long* r = out + 5 * n;
+            r[0] = s.brow_pos;
+            r[1] = s.bcol_pos;
+            r[2] = s.brow_pos != s.bcol_pos ? 0 : (s.is_upper ? 2 : 1);
+            r[3] = (long long)((char*)s.d_value - B.d_buf);
+            r[4] = flag;
+        }
+        ++n;
+    }
+    return n;
+}
+
+// Register, for every block of `table` (a peer's mirror table) that THIS rank owns, a push into the peer's copy.
+// handles128 = the peer's pangulu_sm100_driver_ipc_handles.  Returns the number of pushes registered.
+long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* handles128, const long long* table, long long n)
+{
+    Handle* h = (Handle*)handle;
+    BlockStore& B = h->B;
+    char *peer_buf = nullptr, *peer_sync = nullptr;
+    if (!B.host_only)
+    {
+        ensure_plan(h);
+        pangulu_sm100_ipc_open(handles128, (void**)&peer_buf);
+        pangulu_sm100_ipc_open(handles128 + 64, (void**)&peer_sync);
+    }
+    long long made = 0;
+    for (long long i = 0; i < n; ++i)
+    {
+        const long long* r = table + 5 * i;
+        const eidx brow = (eidx)r[0], bcol = (eidx)r[1];
+        if (B.owner(brow, bcol) != B.rank) continue;
+        int64_t slot = -1;
+        if (r[2] == 0)
+        {
+            const int64_t gid = B.find_block(brow, bcol);
+            if (gid >= 0) slot = B.slot_of_block[gid];
+        }
+        else
+        {
+            slot = B.slot_of_diag[brow];
+            if (slot >= 0 && r[2] == 2) slot += 1;
+        }
+        if (slot < 0)
+        {
+            fprintf(stderr, "[PanguLU ERROR] peer asks for block (%u,%u) that rank %d owns but does not hold\n", brow, bcol, B.rank);
+            exit(EXIT_FAILURE);
+        }
+        if (!B.host_only) pangulu_sm100_plan_add_push(h->plan, B.slots[slot].d_value, peer_buf + r[3], peer_sync + r[4]);
+        ++made;
+    }
+    return made;
+}
+
+void pangulu_sm100_driver_commit(void* handle)
+{
+    Handle* h = (Handle*)handle;
+    if (!h->B.host_only) pangulu_sm100_plan_commit(h->plan);
+}
+
+void pangulu_sm100_driver_gstrf_reset(void* handle) { pangulu_sm100_plan_reset(((Handle*)handle)->plan); }
+void pangulu_sm100_driver_gstrf_launch(void* handle) { pangulu_sm100_plan_launch(((Handle*)handle)->plan); }
 
 long long pangulu_sm100_driver_trace(void* handle, unsigned long long* out, long long cap)
 {

@@ -677,7 +677,13 @@ struct pangulu_sm100_plan
     int* done_init = nullptr;
     int* pending_init = nullptr;
     size_t nids = 0;
+    size_t mega_bytes = 0;
     std::vector<MegaTask> host_tasks;
+    // multi-GPU wiring
+    std::unordered_map<const void*, int> ids;   // device value array -> sync id
+    std::vector<int> h_done_init;
+    std::vector<std::vector<MegaPush<T>>> h_push;  // per sync id
+    void* push_buf = nullptr;
 };
 
 namespace {
@@ -689,7 +695,7 @@ void build_mega(pangulu_sm100_plan* pl)
 {
     Program& P = pl->P;
     const int nb = pl->nb;
-    std::unordered_map<const void*, int> ids;
+    std::unordered_map<const void*, int>& ids = pl->ids;
     auto id_of = [&](const void* p) {
         auto it = ids.find(p);
         if (it != ids.end()) return it->second;
@@ -804,18 +810,30 @@ void build_mega(pangulu_sm100_plan* pl)
     mp.pairs = pl->D.pairs;
     mp.getrf = pl->D.getrf;
     mp.panel = pl->D.panel;
+    mp.push_ptr = nullptr;
+    mp.pushes = nullptr;
+    mp.multi = 0;
     pl->nids = nid;
+    pl->mega_bytes = total;
+    pl->h_done_init = done_init;
+    pl->h_push.assign(nid, {});
     pl->mega = true;
 }
 
-void run_mega(pangulu_sm100_plan* pl)
+void reset_mega(pangulu_sm100_plan* pl)
 {
     MegaParams<T>& mp = pl->mp;
-    if (mp.ntask == 0) return;
+    if (pl->nids == 0) return;
     CK(cudaMemcpyAsync(mp.remaining, pl->remaining_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaMemcpyAsync(mp.done, pl->done_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaMemcpyAsync(mp.pending, pl->pending_init, pl->nids * sizeof(int), cudaMemcpyDeviceToDevice, g.stream));
     CK(cudaMemsetAsync(mp.counter, 0, sizeof(int), g.stream));
+}
+
+void launch_mega(pangulu_sm100_plan* pl)
+{
+    MegaParams<T>& mp = pl->mp;
+    if (mp.ntask == 0) return;
     Timer tm(K_MEGA);
     const size_t smem = (size_t)g.max_smem_optin - 64;
     pl->mp.smem_bytes = smem;  // whole SM: the shared-memory GETRF variant sizes itself against this
@@ -832,6 +850,12 @@ void run_mega(pangulu_sm100_plan* pl)
     }
     CK_LAST();
     g.launches[K_MEGA]++;
+}
+
+void run_mega(pangulu_sm100_plan* pl)
+{
+    reset_mega(pl);
+    launch_mega(pl);
 }
 
 }  // namespace
@@ -1085,7 +1109,75 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
     if (!pl) return;
     if (pl->dev_buf) CK(cudaFree(pl->dev_buf));
     if (pl->mega_buf) CK(cudaFree(pl->mega_buf));
+    if (pl->push_buf) CK(cudaFree(pl->push_buf));
     delete pl;
+}
+
+// ---- multi-GPU wiring of a persistent plan (one rank per GPU, blocks pushed to peers over NVLink) -------------
+void* pangulu_sm100_plan_sync_base(pangulu_sm100_plan* pl, size_t* bytes)
+{
+    if (!pl || !pl->mega) return nullptr;
+    if (bytes) *bytes = pl->mega_bytes;
+    return pl->mega_buf;
+}
+long long pangulu_sm100_plan_flag_offset(pangulu_sm100_plan* pl, const void* d_value)
+{
+    if (!pl || !pl->mega) return -1;
+    auto it = pl->ids.find(d_value);
+    if (it == pl->ids.end()) return -1;
+    return (long long)((char*)(pl->mp.done + it->second) - (char*)pl->mega_buf);
+}
+void pangulu_sm100_plan_expect_remote(pangulu_sm100_plan* pl, const void* d_value)
+{
+    auto it = pl->ids.find(d_value);
+    if (it != pl->ids.end()) pl->h_done_init[it->second] = 0;
+}
+void pangulu_sm100_plan_add_push(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag)
+{
+    auto it = pl->ids.find(d_value_local);
+    if (it == pl->ids.end()) return;  // the block is not produced or referenced by this plan
+    MegaPush<T> e;
+    e.peer_val = (T*)peer_value;
+    e.peer_flag = (int*)peer_flag;
+    pl->h_push[it->second].push_back(e);
+}
+void pangulu_sm100_plan_commit(pangulu_sm100_plan* pl)
+{
+    if (!pl || !pl->mega) return;
+    CK(cudaMemcpy(pl->done_init, pl->h_done_init.data(), pl->nids * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> ptr(pl->nids + 1, 0);
+    std::vector<MegaPush<T>> flat;
+    for (size_t i = 0; i < pl->nids; ++i)
+    {
+        ptr[i] = (int)flat.size();
+        flat.insert(flat.end(), pl->h_push[i].begin(), pl->h_push[i].end());
+    }
+    ptr[pl->nids] = (int)flat.size();
+    if (pl->push_buf) CK(cudaFree(pl->push_buf));
+    const size_t b0 = (ptr.size() * sizeof(int) + 255) & ~(size_t)255;
+    CK(cudaMalloc(&pl->push_buf, b0 + flat.size() * sizeof(MegaPush<T>) + 256));
+    CK(cudaMemcpy(pl->push_buf, ptr.data(), ptr.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (!flat.empty()) CK(cudaMemcpy((char*)pl->push_buf + b0, flat.data(), flat.size() * sizeof(MegaPush<T>), cudaMemcpyHostToDevice));
+    pl->mp.push_ptr = (const int*)pl->push_buf;
+    pl->mp.pushes = (const MegaPush<T>*)((char*)pl->push_buf + b0);
+    pl->mp.multi = 1;
+}
+void pangulu_sm100_plan_reset(pangulu_sm100_plan* pl) { if (pl && pl->mega) reset_mega(pl); }
+void pangulu_sm100_plan_launch(pangulu_sm100_plan* pl) { if (pl && pl->mega) launch_mega(pl); }
+int pangulu_sm100_ipc_export(void* devptr, void* handle64)
+{
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, devptr));
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+int pangulu_sm100_ipc_open(const void* handle64, void** devptr)
+{
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CK(cudaIpcOpenMemHandle(devptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
 }
 
 void pangulu_sm100_stats_reset(void)

@@ -1085,6 +1085,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 // running CTA, so the spin waits cannot deadlock.
 // ================================================================================================
 struct MegaTask { int kind, a, b, c; };
+template <class T> struct MegaPush { T* peer_val; int* peer_flag; };
 enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5 };
 
 template <class T>
@@ -1106,6 +1107,11 @@ struct MegaParams
     int* counter;           // ticket
     T* scratch;             // dense GETRF tile per CTA
     size_t smem_bytes;      // dynamic shared memory the kernel was launched with
+    // multi-GPU: blocks finalised here that other ranks read are written straight into the peers' mirror copies
+    // over NVLink (peer-mapped pointers), followed by a system-scope release of the peer's done flag
+    const int* push_ptr;    // per sync id: range into pushes[] (null when single-GPU)
+    const MegaPush<T>* pushes;
+    int multi;              // 1: flags may be written by peers -> system-scope acquire
     unsigned long long* trace;  // optional: per task {fetch, start, end} in ns (globaltimer), else null
 };
 __device__ __forceinline__ unsigned long long global_ns()
@@ -1122,10 +1128,38 @@ __device__ __forceinline__ int ld_acquire(const int* p)
     return v;
 }
 __device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ void spin_until_set(const int* flag)
+__device__ __forceinline__ int ld_acquire_sys(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void spin_until_set(const int* flag, int multi = 0)
 {
     unsigned ns = 20;
-    while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+    if (multi)
+        while (ld_acquire_sys(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+    else
+        while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+}
+// Whole CTA: copy the n finished values of a block into every peer mirror registered for sync id `id`, then raise
+// the peers' done flags.  Peer pointers are NVLink-mapped device pointers of other GPUs (CUDA IPC).
+template <class T>
+__device__ __forceinline__ void push_block(const int* push_ptr, const MegaPush<T>* pushes, int id, const T* src, u32 n)
+{
+    if (!push_ptr) return;
+    const int e0 = push_ptr[id], e1 = push_ptr[id + 1];
+    if (e0 == e1) return;
+    for (int e = e0; e < e1; ++e)
+    {
+        T* dst = pushes[e].peer_val;
+        for (u32 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int e = e0; e < e1; ++e) st_release_sys(pushes[e].peer_flag, 1);
 }
 __device__ __forceinline__ void spin_until_zero(const int* cnt)
 {
@@ -1157,6 +1191,7 @@ mega_kernel(const MegaParams<T> P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
+    __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid / PSM_WARP;
     const int nb = P.nb;
     for (;;)
@@ -1177,8 +1212,8 @@ mega_kernel(const MegaParams<T> P)
                 for (u32 p = D.pair_begin; p < D.pair_end; ++p)
                 {
                     const int2 dep = P.pair_dep[p];
-                    spin_until_set(P.done + dep.x);
-                    spin_until_set(P.done + dep.y);
+                    spin_until_set(P.done + dep.x, P.multi);
+                    spin_until_set(P.done + dep.y, P.multi);
                 }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
@@ -1220,13 +1255,15 @@ mega_kernel(const MegaParams<T> P)
             __threadfence();
             __syncthreads();
             if (tid == 0) { st_release(P.done + id.x, 1); st_release(P.done + id.y, 1); }
+            push_block<T>(P.push_ptr, P.pushes, id.x, G.lower.val, G.lower.ptr[nb]);
+            push_block<T>(P.push_ptr, P.pushes, id.y, G.upper.val, G.upper.ptr[nb]);
             break;
         }
         case MEGA_PANEL:
         {
             const PanelTask<T> Q = P.panel[mt.a];
             const int2 id = P.panel_id[mt.a];
-            if (tid == 0) { spin_until_set(P.done + id.y); spin_until_zero(P.remaining + id.x); }
+            if (tid == 0) { spin_until_set(P.done + id.y, P.multi); spin_until_zero(P.remaining + id.x); }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             // one task = 64 consecutive rows/columns of the block (four per warp); the diagonal half they are solved
@@ -1258,7 +1295,13 @@ mega_kernel(const MegaParams<T> P)
             for (int rc = mt.b + warp; rc < mt.b + 64 && rc < nb; rc += 16) panel_solve_line<T>(nb, Q2, rc, x);
             __threadfence();
             __syncthreads();
-            if (tid == 0 && atomicSub(P.pending + id.x, 1) == 1) { __threadfence(); st_release(P.done + id.x, 1); }
+            if (tid == 0)
+            {
+                s_last = atomicSub(P.pending + id.x, 1) == 1;
+                if (s_last) { __threadfence(); st_release(P.done + id.x, 1); }
+            }
+            __syncthreads();
+            if (s_last) push_block<T>(P.push_ptr, P.pushes, id.x, Q.b.val, Q.b.ptr[nb]);
             break;
         }
         }

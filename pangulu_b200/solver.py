@@ -64,6 +64,7 @@ class PanguLU:
         self.vtype = DTYPE_TO_VTYPE[self.dtype]
         self.L = _lib.load(self.vtype)
         self.n = A.shape[0]
+        self._host_only = bool(host_only)
         driver_config(self.vtype, ordering=ordering, mode=mode, rank=rank, nproc=nproc, host_only=int(host_only),
                       verbose=int(verbose), schedule=schedule, lookahead=lookahead)
         self._colptr = np.ascontiguousarray(A.indptr, dtype=np.uint64)
@@ -117,6 +118,42 @@ class PanguLU:
 
     def download(self) -> None:
         self.L.pangulu_sm100_driver_download(self._h)
+
+    # -- multi-GPU wiring ---------------------------------------------------------------------------------
+    def mirror_table(self) -> np.ndarray:
+        """int64[n, 5]: remote blocks this rank reads (brow, bcol, kind, value offset, flag offset)."""
+        n = int(self.L.pangulu_sm100_driver_mirror_table(self._h, None, 0))
+        out = np.zeros((max(n, 1), 5), dtype=np.int64)
+        self.L.pangulu_sm100_driver_mirror_table(self._h, out.ctypes.data, n)
+        return out[:n]
+
+    def ipc_handles(self) -> bytes:
+        buf = (C.c_ubyte * 128)()
+        self.L.pangulu_sm100_driver_ipc_handles(self._h, buf)
+        return bytes(buf)
+
+    def connect(self, group=None) -> int:
+        """Wire this rank's plan to all peers of a torch.distributed group (one rank per GPU): exchange CUDA IPC
+        handles and mirror tables, register the NVLink pushes, install the barrier.  Returns the pushes registered."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        table = self.mirror_table()
+        handles = self.ipc_handles() if not self._host_only else bytes(128)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (handles, table), group=group)
+        made = 0
+        for r, (hd, tb) in enumerate(gathered):
+            if r == rank or len(tb) == 0:
+                continue
+            tb = np.ascontiguousarray(tb, dtype=np.int64)
+            hb = (C.c_ubyte * 128).from_buffer_copy(hd)
+            made += int(self.L.pangulu_sm100_driver_connect_peer(self._h, hb, tb.ctypes.data, len(tb)))
+        self.L.pangulu_sm100_driver_commit(self._h)
+        self._barrier_cb = C.CFUNCTYPE(None)(lambda: dist.barrier(group))
+        self.L.pangulu_sm100_driver_set_barrier(C.cast(self._barrier_cb, C.c_void_p))
+        dist.barrier(group)
+        return made
 
     def factor_check(self) -> float:
         return float(self.L.pangulu_sm100_driver_factor_check(self._h))
