@@ -47,7 +47,8 @@ void pangulu_gstrs(sparse_value_t *rhs, pangulu_gstrs_options *gstrs_options, vo
 void pangulu_gssv(sparse_value_t *rhs, pangulu_gstrf_options *gstrf_options, pangulu_gstrs_options *gstrs_options, void **pangulu_handle);
 void pangulu_finalize(void **pangulu_handle);
 
-/* Driver options, set BEFORE pangulu_init (the reference takes rank/size from MPI_COMM_WORLD):
+/* Driver options, set BEFORE pangulu_init; a handle keeps the values it was created with (the reference takes
+ * rank/size from MPI_COMM_WORLD):
  *   "rank", "nproc"   position in the p x q rank grid (one rank per GPU)
  *   "ordering"        0 natural (input already permuted), 1 METIS_NodeND, -1 (default) METIS when built in
  *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan
@@ -70,6 +71,8 @@ pangulu_storage_slot_t *pangulu_sm100_driver_slot(void *handle, long long i);
 const void *pangulu_sm100_driver_perm(void *handle, int which);
 /* the static schedule: tasks sorted by wave, wave_ptr has nwave+1 entries */
 const pangulu_task_t *pangulu_sm100_driver_tasks(void *handle, const pangulu_uint64_t **wave_ptr);
+/* switch an initialised handle between the two gstrf modes (0 reference-facing, 1 resident plan) */
+void pangulu_sm100_driver_set_mode(void *handle, int mode);
 /* put the values of A back into the host block buffers (and the device copy) so gstrf can run again */
 void pangulu_sm100_driver_reset_values(void *handle, int also_device);
 /* resident mode: enqueue the whole factorisation on the module's stream (pangulu_sm100_stream()) without

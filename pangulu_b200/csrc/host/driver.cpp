@@ -52,6 +52,7 @@ struct Handle
     WorkModel work;
     pangulu_sm100_plan* plan = nullptr;
     int mode = 0;
+    int rank = 0, nproc = 1;  // fixed at pangulu_init (later driver_config calls configure FUTURE handles only)
     bool factored = false;
     std::map<std::string, double> times;
 };
@@ -116,6 +117,8 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     }
     h->n = pangulu_n;
     h->mode = (int)g_cfg.mode;
+    h->rank = (int)g_cfg.rank;
+    h->nproc = (int)g_cfg.nproc;
 
     // one rank <-> one GPU: rank % device_count (src/pangulu.c:126-130)
     h->B.host_only = g_cfg.host_only != 0;
@@ -183,8 +186,7 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         fprintf(stderr, "[PanguLU ERROR] handle was created in host_only (structure) mode; numeric factorisation needs the GPU -- there is no CPU path\n");
         exit(EXIT_FAILURE);
     }
-    h->mode = (int)g_cfg.mode;  // the mode may be switched between calls (bench.py times both on one handle)
-    if (g_cfg.nproc > 1) h->mode = 1;
+    if (h->nproc > 1) h->mode = 1;  // (the mode of a handle can be switched with pangulu_sm100_driver_set_mode)
     if (h->mode == 1 && !h->plan)
     {
         const double tp = wall_seconds();
@@ -193,7 +195,7 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         h->times["plan"] = wall_seconds() - tp;
     }
     const double t0 = wall_seconds();
-    if (g_cfg.nproc > 1)
+    if (h->nproc > 1)
     {
         // one rank per GPU: the plan must have been wired to the peers (pangulu_sm100_driver_connect_peer/commit);
         // every rank clears its flags, all ranks meet, then the persistent kernels run and push blocks to each other
@@ -346,6 +348,8 @@ const pangulu_task_t* pangulu_sm100_driver_tasks(void* handle, const pangulu_uin
     if (wave_ptr) *wave_ptr = (const pangulu_uint64_t*)h->sched.wave_ptr.data();
     return h->sched.tasks.data();
 }
+
+void pangulu_sm100_driver_set_mode(void* handle, int mode) { ((Handle*)handle)->mode = mode; }
 
 void pangulu_sm100_driver_reset_values(void* handle, int also_device)
 {

@@ -114,7 +114,7 @@ class PanguLU:
         self.L.platform("synchronize")()
 
     def set_mode(self, mode: int) -> None:
-        driver_config(self.vtype, mode=mode)
+        self.L.pangulu_sm100_driver_set_mode(self._h, int(mode))
 
     def download(self) -> None:
         self.L.pangulu_sm100_driver_download(self._h)
