@@ -68,13 +68,14 @@ def main(argv=None):
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-blocks", action="store_true")
     ap.add_argument("--nthread", type=int, default=1)
+    ap.add_argument("--flavour", default="cpu", help="cpu: reference CPU platform; gpu: reference host code on top of the sm_100a module")
     a = ap.parse_args(argv)
     sys.path.insert(0, _ROOT)
     from oracle.ref import RefLib
 
     z = np.load(a.inp)
     n = int(z["n"])
-    R = RefLib(a.vtype, perf=a.perf)
+    R = RefLib(a.vtype, perf=a.perf, flavour=a.flavour)
     f = R.factor(n, z["indptr"], z["indices"], z["data"], a.nb, nthread=a.nthread)
     out = {"n": n, "nb": f.nb, "symbolic_nnz": f.symbolic_nnz, "has_metis": int(R.has_metis), "has_mc64": int(R.has_mc64)}
     out.update(f.perms())
@@ -97,7 +98,7 @@ def main(argv=None):
     np.savez(a.out, **out)
 
 
-def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthread=1, quiet=True):
+def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthread=1, quiet=True, flavour="cpu"):
     """Factor scipy CSC matrix A with the reference in a subprocess; returns the loaded npz dict."""
     import scipy.sparse as sp
 
@@ -106,7 +107,8 @@ def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthre
     with tempfile.TemporaryDirectory() as td:
         inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
         np.savez(inp, indptr=A.indptr.astype(np.uint64), indices=A.indices.astype(np.uint32), data=A.data, n=A.shape[0])
-        cmd = [sys.executable, "-m", "oracle.ref_run", inp, out, "--nb", str(nb), "--vtype", vtype, "--nthread", str(nthread)]
+        cmd = [sys.executable, "-m", "oracle.ref_run", inp, out, "--nb", str(nb), "--vtype", vtype, "--nthread", str(nthread),
+               "--flavour", flavour]
         if perf:
             cmd.append("--perf")
         if not solve:

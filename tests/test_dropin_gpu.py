@@ -1,0 +1,43 @@
+"""Drop-in check on the GPU: the UNMODIFIED reference host code (pangulu_init / pangulu_gstrf / pangulu_gstrs, its
+dynamic scheduler, block storage, kernel interface and generated platform dispatch, compiled with -DGPU_OPEN) running on
+top of this module, whose object file takes the place of the stock CUDA platform (oracle/_ref/libpangulu_ref_gpu_*.so,
+built by oracle/Makefile with -DPANGULU_SM100_ID=0201000).  Expected: same structure, same permutation, L/U values
+within tolerance of the reference's own CPU platform, residual no worse."""
+import numpy as np
+import pytest
+
+from helpers import TOL, rel_err, trefethen_matrix
+from pangulu_b200 import matrices
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("trefethen-nb4", lambda: trefethen_matrix(), 4),
+    ("trefethen-nb10", lambda: trefethen_matrix(), 10),
+    ("poisson3d-12-nb32", lambda: matrices.poisson3d(12), 32),
+    ("laplace2d-48-nb64", lambda: matrices.laplace2d(48), 64),
+    ("stencil27-8-nb128", lambda: matrices.stencil27(8), 128),
+]
+
+
+@pytest.mark.parametrize("name,make,nb", CASES, ids=[c[0] for c in CASES])
+def test_reference_scheduler_on_sm100_platform(name, make, nb):
+    from oracle.ref import ref_available
+    from oracle.ref_run import run_reference, unflatten
+
+    if not (ref_available("r64", flavour="gpu") and ref_available("r64", flavour="cpu")):
+        pytest.skip("oracle/_ref GPU/CPU reference builds not present on this box")
+    A = make()
+    cpu = run_reference(A, nb, flavour="cpu")
+    gpu = run_reference(A, nb, flavour="gpu")
+    assert np.array_equal(cpu["metis_perm"], gpu["metis_perm"])
+    want, got = unflatten(cpu, "post_", nb), unflatten(gpu, "post_", nb)
+    assert len(want) == len(got)
+    worst = 0.0
+    for g, w in zip(got, want):
+        assert (g.brow, g.bcol, g.is_upper) == (w.brow, w.bcol, w.is_upper)
+        assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)
+        assert np.isfinite(g.value).all()
+        worst = max(worst, rel_err(g.value, w.value))
+    assert worst <= TOL["r64"], worst
+    assert float(gpu["resid"]) <= max(4 * float(cpu["resid"]), 1e-15)
