@@ -45,7 +45,9 @@ inline size_t align16(size_t x) { return (x + 15u) & ~(size_t)15u; }
 // meaning of every array is exactly the reference's; only the placement differs from the interleaved
 // wire layout of SURVEY Appendix A, which this driver does not need because every rank derives the
 // patterns itself and ships values only.)
-inline size_t value_bytes(size_t nnz) { return align16(sizeof(T) * nnz); }
+// (an empty block -- e.g. the strict-lower half of a diagonal-only diagonal block -- still gets its own 16 bytes: the
+// platform identifies a block by its value pointer, which therefore must be unique)
+inline size_t value_bytes(size_t nnz) { return align16(sizeof(T) * std::max<size_t>(nnz, 1)); }
 inline size_t index_bytes(int nb, size_t nnz, bool mirror)
 {
     size_t s = align16(sizeof(iptr) * (size_t)(nb + 1)) + align16(sizeof(iidx) * nnz);

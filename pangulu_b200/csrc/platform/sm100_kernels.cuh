@@ -1255,7 +1255,9 @@ mega_kernel(const MegaParams<T> P)
             __threadfence();
             __syncthreads();
             if (tid == 0) { st_release(P.done + id.x, 1); st_release(P.done + id.y, 1); }
-            push_block<T>(P.push_ptr, P.pushes, id.x, G.lower.val, G.lower.ptr[nb]);
+            // (two halves with one sync id = an empty lower half sharing its value pointer with the upper one: a single
+            // push, after which the flag may be raised)
+            if (id.x != id.y) push_block<T>(P.push_ptr, P.pushes, id.x, G.lower.val, G.lower.ptr[nb]);
             push_block<T>(P.push_ptr, P.pushes, id.y, G.upper.val, G.upper.ptr[nb]);
             break;
         }
