@@ -46,7 +46,7 @@ typedef calculate_type T;
     } while (0)
 #define CK_LAST() CK(cudaGetLastError())
 
-enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_MEGA = 6, K_NCLASS = 7 };
+enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_MEGA = 6, K_SSSSM_CTILE = 7, K_NCLASS = 8 };
 enum { K_GETRF_SMEM = 100, K_GETRF_DENSE = 101 };  // step kinds only; accounted under K_GETRF
 
 struct Options
@@ -60,6 +60,8 @@ struct Options
     long long split_pairs = 1;  // split heavy destinations of thin waves over several CTAs
     long long trace = 0;        // persistent executor: record per-task fetch/start/end timestamps (pangulu_sm100_plan_trace)
     long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
+    long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
+    long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -79,8 +81,8 @@ struct Ctx
     cudaStream_t stream = nullptr;
     Options opt;
     std::vector<Slab> slabs;
-    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0};
-    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0};
+    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int max_smem_optin = 0;
     int sm_count = 0;
@@ -197,8 +199,10 @@ struct Program
 {
     std::vector<GetrfTask<T>> getrf;
     std::vector<PanelTask<T>> panel;
+    std::vector<const pangulu_storage_slot_t*> panel_slot;  // destination slot of each panel task
     std::vector<SsssmDest<T>> dests;
     std::vector<SsssmPair<T>> pairs;
+    std::vector<CPair> cpairs;        // operand pairs of the compact-tile destinations
     std::vector<Step> steps;
     std::vector<Download> downloads;  // referenced by steps of kind -1 (off/count)
 };
@@ -209,11 +213,90 @@ struct DevProgram
     PanelTask<T>* panel = nullptr;
     SsssmDest<T>* dests = nullptr;
     SsssmPair<T>* pairs = nullptr;
+    CPair* cpairs = nullptr;
+    DenseOp<T>* ops = nullptr;
+};
+
+// Registry of the compact dense operand copies of one plan (sm100_compact.cuh): which blocks have one, their row /
+// column lists, and where the copy lives.  Everything is derived from the (immutable) pattern in the host slot.
+struct DenseReg
+{
+    struct Entry
+    {
+        const pangulu_storage_slot_t* slot;
+        u32 cnt, ld, kmask;
+        size_t dense_off, dense_len;  // in values
+        size_t meta_off;              // in u16: list[cnt] then inv[nb]
+        u16 tile_start[18];
+    };
+    int nb = 0;
+    std::vector<Entry> entries;
+    std::unordered_map<const pangulu_storage_slot_t*, int> index;
+    std::vector<u16> meta;
+    size_t dense_total = 0;
+
+    int find(const pangulu_storage_slot_t* s) const
+    {
+        auto it = index.find(s);
+        return it == index.end() ? -1 : it->second;
+    }
+    // as_b = false: block of the L panel used as the left operand (rows compacted); true: block of the U panel
+    int get(const pangulu_storage_slot_t* s, bool as_b)
+    {
+        auto it = index.find(s);
+        if (it != index.end()) return it->second;
+        Entry e;
+        memset(&e, 0, sizeof e);
+        e.slot = s;
+        const u32* cp = s->columnpointer;
+        const u16* ri = s->rowindex;
+        const u32 nnz = cp[nb];
+        std::vector<u16> list, inv((size_t)nb, (u16)0xffff);
+        u32 kmask = 0;
+        if (!as_b)
+        {
+            std::vector<char> present((size_t)nb, 0);
+            for (u32 q = 0; q < nnz; ++q) present[ri[q]] = 1;
+            for (int r = 0; r < nb; ++r)
+                if (present[r]) { inv[r] = (u16)list.size(); list.push_back((u16)r); }
+            for (int c = 0; c < nb; ++c)
+                if (cp[c + 1] > (c == 0 ? 0u : cp[c])) kmask |= 1u << (c / PSM_CT_KC);
+            e.cnt = (u32)list.size();
+            e.ld = ((e.cnt + 7u) & ~7u) + 4u;
+            e.dense_len = (size_t)nb * e.ld;
+        }
+        else
+        {
+            for (int c = 0; c < nb; ++c)
+                if (cp[c + 1] > (c == 0 ? 0u : cp[c])) { inv[c] = (u16)list.size(); list.push_back((u16)c); }
+            for (u32 q = 0; q < nnz; ++q) kmask |= 1u << (ri[q] / PSM_CT_KC);
+            e.cnt = (u32)list.size();
+            e.ld = PSM_CT_BLD;
+            e.dense_len = (size_t)(nb / PSM_CT_KC) * e.cnt * PSM_CT_BLD;
+            u32 run = 0;
+            size_t li = 0;
+            for (int t = 0; t <= nb / 16; ++t)
+            {
+                while (li < list.size() && list[li] < 16 * t) { ++li; ++run; }
+                e.tile_start[t] = (u16)run;
+            }
+        }
+        e.kmask = kmask;
+        e.dense_off = dense_total;
+        dense_total += (e.dense_len + 3) & ~(size_t)3;  // keeps every copy 16-byte aligned for all value types
+        e.meta_off = meta.size();
+        meta.insert(meta.end(), list.begin(), list.end());
+        meta.insert(meta.end(), inv.begin(), inv.end());
+        const int id = (int)entries.size();
+        entries.push_back(e);
+        index.emplace(s, id);
+        return id;
+    }
 };
 
 // Append the tasks [t0,t1) -- executed in array order like the reference's serial loop
 // (pangulu_platform_0201000.cu:880-897) -- as maximal runs of one kernel class.
-void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, size_t t1, bool eager_download)
+void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, size_t t1, bool eager_download, DenseReg* reg = nullptr)
 {
     size_t i = t0;
     std::vector<size_t> order;
@@ -234,12 +317,18 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             const bool tile_ok = nb >= 32 && nb <= 256 && mode != 1;
             const double thr = (double)g.opt.dense_threshold / 1000.0;
             const double nb4thr2 = thr * thr * (double)nb * nb * (double)nb * nb;
+            // compact path (plans only): both operands are owned blocks (a mirrored block of another rank has no compact
+            // copy on this rank) and the pair is not too sparse
+            const bool compact_ok = reg && g.opt.compact != 0 && nb % 16 == 0 && nb >= 32 && nb <= 256;
+            const double cthr = (double)g.opt.compact_threshold / 1000.0;
+            const double nb4cthr2 = cthr * cthr * (double)nb * nb * (double)nb * nb;
             for (size_t k = 0; k < nrun; ++k)
             {
                 order[k] = k;
                 const pangulu_task_t& t = tasks[i + k];
                 const double na = slot_nnz(nb, t.op1), nbn = slot_nnz(nb, t.op2);
-                cls[k] = (tile_ok && (mode == 2 || na * nbn >= nb4thr2)) ? 0 : 1;
+                if (compact_ok && t.op1->bin_id == 0 && t.op2->bin_id == 0 && na * nbn >= nb4cthr2) cls[k] = 2;
+                else cls[k] = (tile_ok && (mode == 2 || na * nbn >= nb4thr2)) ? 0 : 1;
             }
             auto key = [&](size_t k) -> const void* {
                 pangulu_storage_slot_t* d = tasks[i + k].opdst;
@@ -253,7 +342,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 const size_t fa = first_seen[key(a)], fb = first_seen[key(b)];
                 return fa != fb ? fa < fb : cls[a] < cls[b];
             });
-            std::vector<SsssmDest<T>> by_cls[2];
+            std::vector<SsssmDest<T>> by_cls[3];
             const void* cur = nullptr;
             int cur_cls = -1;
             for (size_t k : order)
@@ -280,9 +369,18 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                         D.c = blk_csc(d);
                         D.nnz_c = slot_nnz(nb, d);
                     }
-                    D.pair_begin = (u32)P.pairs.size();
+                    D.pair_begin = (u32)(cur_cls == 2 ? P.cpairs.size() : P.pairs.size());
                     D.pair_end = D.pair_begin;
                     by_cls[cur_cls].push_back(D);
+                }
+                if (cur_cls == 2)
+                {
+                    CPair cp;
+                    cp.a = reg->get(t.op1, false);
+                    cp.b = reg->get(t.op2, true);
+                    P.cpairs.push_back(cp);
+                    by_cls[cur_cls].back().pair_end = (u32)P.cpairs.size();
+                    continue;
                 }
                 SsssmPair<T> pr;
                 pr.a = blk_ro(t.op1);
@@ -318,7 +416,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                     by_cls[0].swap(split);
                 }
             }
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < 3; ++c)
             {
                 if (by_cls[c].empty()) continue;
                 // per-wave launches: heaviest destinations first (the grid is consumed in order, this trims the tail);
@@ -328,7 +426,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                         return (x.pair_end - x.pair_begin) > (y.pair_end - y.pair_begin);
                     });
                 Step st;
-                st.kind = c == 0 ? K_SSSSM_TILE : K_SSSSM_SPARSE;
+                st.kind = c == 0 ? K_SSSSM_TILE : c == 1 ? K_SSSSM_SPARSE : K_SSSSM_CTILE;
                 st.off = P.dests.size();
                 st.count = by_cls[c].size();
                 P.dests.insert(P.dests.end(), by_cls[c].begin(), by_cls[c].end());
@@ -393,6 +491,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 PanelTask<T> Q;
                 memset(&Q, 0, sizeof Q);
                 Q.kind = t.kernel_id;
+                Q.dense = -1;
                 Q.b = blk_csc(t.opdst);
                 if (t.kernel_id == PANGULU_TASK_TSTRF)
                 {
@@ -404,6 +503,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                     Q.diag = blk_csc(lo);
                 }
                 P.panel.push_back(Q);
+                P.panel_slot.push_back(t.opdst);
                 st.count++;
                 if (eager_download)
                 {
@@ -530,22 +630,35 @@ void launch_ssssm_tile(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, siz
     g.launches[K_SSSSM_TILE]++;
 }
 
-template <int WARPS> void launch_panel_w(int nb, const PanelTask<T>* t, size_t n)
+void launch_ssssm_ctile(int nb, const SsssmDest<T>* d, const CPair* cp, const DenseOp<T>* ops, size_t ndest)
+{
+    if (!ndest) return;
+    Timer tm(K_SSSSM_CTILE);
+    constexpr int TN = ct_traits<T>::TN;
+    const int tiles = (nb + TN - 1) / TN;
+    const size_t smem = CtLayout<T, TN, ct_traits<T>::STAGES>::total;
+    set_smem(ssssm_ctile_kernel<T>, smem);
+    ssssm_ctile_kernel<T><<<(unsigned)(ndest * tiles), 512, smem, g.stream>>>(nb, d, cp, ops, tiles);
+    CK_LAST();
+    g.launches[K_SSSSM_CTILE]++;
+}
+
+template <int WARPS> void launch_panel_w(int nb, const PanelTask<T>* t, size_t n, const DenseOp<T>* ops)
 {
     const int groups = (nb + WARPS - 1) / WARPS;
     const size_t smem = (size_t)WARPS * nb * sizeof(T);
     set_smem(panel_solve_kernel<T, WARPS>, smem);
-    panel_solve_kernel<T, WARPS><<<(unsigned)(n * groups), WARPS * PSM_WARP, smem, g.stream>>>(nb, t, groups);
+    panel_solve_kernel<T, WARPS><<<(unsigned)(n * groups), WARPS * PSM_WARP, smem, g.stream>>>(nb, t, groups, ops);
     CK_LAST();
 }
-void launch_panel(int nb, const PanelTask<T>* t, size_t n)
+void launch_panel(int nb, const PanelTask<T>* t, size_t n, const DenseOp<T>* ops)
 {
     if (!n) return;
     Timer tm(K_TSTRF);
     const size_t per_warp = (size_t)nb * sizeof(T);
-    if (8 * per_warp <= (size_t)g.max_smem_optin / 2) launch_panel_w<8>(nb, t, n);
-    else if (4 * per_warp <= (size_t)g.max_smem_optin) launch_panel_w<4>(nb, t, n);
-    else launch_panel_w<1>(nb, t, n);
+    if (8 * per_warp <= (size_t)g.max_smem_optin / 2) launch_panel_w<8>(nb, t, n, ops);
+    else if (4 * per_warp <= (size_t)g.max_smem_optin) launch_panel_w<4>(nb, t, n, ops);
+    else launch_panel_w<1>(nb, t, n, ops);
     g.launches[K_TSTRF]++;
 }
 
@@ -606,10 +719,11 @@ void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t 
         {
         case K_SSSSM_SPARSE: launch_ssssm_sparse(nb, D.dests + st.off, D.pairs, st.count); break;
         case K_SSSSM_TILE: launch_ssssm_tile(nb, D.dests + st.off, D.pairs, st.count); break;
+        case K_SSSSM_CTILE: launch_ssssm_ctile(nb, D.dests + st.off, D.cpairs, D.ops, st.count); break;
         case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); break;
         case K_GETRF_SMEM: launch_getrf_smem(nb, D.getrf + st.off, st.count, st.smem); break;
         case K_GETRF_DENSE: launch_getrf_dense(nb, D.getrf + st.off, st.count); break;
-        case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count); break;
+        case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count, D.ops); break;
         case -1:
             for (size_t k = st.off; k < st.off + st.count; ++k)
                 CK(cudaMemcpyAsync(P.downloads[k].h, P.downloads[k].d, P.downloads[k].bytes, cudaMemcpyDeviceToHost, g.stream));
@@ -669,6 +783,11 @@ struct pangulu_sm100_plan
     DevProgram D;
     std::vector<size_t> wave_step;  // wave w -> first step
     void* dev_buf;
+    // compact dense operand copies
+    DenseReg reg;
+    void* dense_buf = nullptr;   // values (zero-filled once; structural zeros stay zero)
+    void* dense_meta = nullptr;  // row / column lists and inverse maps
+    std::vector<const void*> op_val;  // per compact copy: device value array of the block it mirrors (sync id key)
     // persistent executor
     bool mega = false;
     void* mega_buf = nullptr;
@@ -705,7 +824,7 @@ void build_mega(pangulu_sm100_plan* pl)
     };
     std::vector<MegaTask> tasks;
     std::vector<int> dest_id(P.dests.size(), 0), remaining, pending;
-    std::vector<int2> pair_dep(P.pairs.size()), getrf_id(P.getrf.size()), panel_id(P.panel.size());
+    std::vector<int2> pair_dep(P.pairs.size()), getrf_id(P.getrf.size()), panel_id(P.panel.size()), cpair_dep(P.cpairs.size());
     std::vector<char> produced;
     auto touch = [&](int id) {
         if ((size_t)id >= remaining.size()) { remaining.resize(id + 1, 0); produced.resize(id + 1, 0); pending.resize(id + 1, 0); }
@@ -716,7 +835,14 @@ void build_mega(pangulu_sm100_plan* pl)
         touch(pair_dep[p].x);
         touch(pair_dep[p].y);
     }
+    for (size_t p = 0; p < P.cpairs.size(); ++p)
+    {
+        cpair_dep[p] = make_int2(id_of(pl->op_val[P.cpairs[p].a]), id_of(pl->op_val[P.cpairs[p].b]));
+        touch(cpair_dep[p].x);
+        touch(cpair_dep[p].y);
+    }
     const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
+    const int ctiles = (nb + ct_traits<T>::TN - 1) / ct_traits<T>::TN;
     const int sgroup = 64, sgroups = (nb + sgroup - 1) / sgroup;
     for (const Step& st : P.steps)
     {
@@ -724,12 +850,18 @@ void build_mega(pangulu_sm100_plan* pl)
         {
         case K_SSSSM_TILE:
         case K_SSSSM_SPARSE:
+        case K_SSSSM_CTILE:
             for (size_t d = st.off; d < st.off + st.count; ++d)
             {
                 const int id = id_of(P.dests[d].c.val);
                 touch(id);
                 dest_id[d] = id;
-                if (st.kind == K_SSSSM_TILE)
+                if (st.kind == K_SSSSM_CTILE)
+                {
+                    for (int t = 0; t < ctiles; ++t) tasks.push_back({MEGA_CTILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
+                    remaining[id] += ctiles;
+                }
+                else if (st.kind == K_SSSSM_TILE)
                 {
                     for (int t = 0; t < tiles; ++t) tasks.push_back({MEGA_TILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
                     remaining[id] += tiles;
@@ -773,11 +905,11 @@ void build_mega(pangulu_sm100_plan* pl)
     for (size_t i = 0; i < nid; ++i) done_init[i] = produced[i] ? 0 : 1;  // blocks no task of this plan produces are final already
 
     const int nbp = (nb + 31) & ~31;
-    const size_t sz_tasks = vbytes(tasks), sz_pd = vbytes(pair_dep), sz_di = vbytes(dest_id), sz_gi = vbytes(getrf_id), sz_pi = vbytes(panel_id);
+    const size_t sz_tasks = vbytes(tasks), sz_pd = vbytes(pair_dep), sz_di = vbytes(dest_id), sz_gi = vbytes(getrf_id), sz_pi = vbytes(panel_id), sz_cd = vbytes(cpair_dep);
     const size_t sz_ids = (nid * sizeof(int) + 255) & ~(size_t)255;
     const size_t sz_scratch = ((size_t)g.sm_count * nbp * nbp * sizeof(T) + 255) & ~(size_t)255;
     const size_t sz_trace = g.opt.trace ? ((tasks.size() * 3 * sizeof(unsigned long long) + 255) & ~(size_t)255) : 0;
-    const size_t total = sz_tasks + sz_pd + sz_di + sz_gi + sz_pi + 6 * sz_ids + 256 + sz_scratch + sz_trace;
+    const size_t total = sz_tasks + sz_pd + sz_di + sz_gi + sz_pi + sz_cd + 6 * sz_ids + 256 + sz_scratch + sz_trace;
     char* d = nullptr;
     CK(cudaMalloc((void**)&d, total));
     pl->mega_buf = d;
@@ -796,6 +928,9 @@ void build_mega(pangulu_sm100_plan* pl)
     mp.dest_id = (const int*)put(dest_id.data(), dest_id.size() * sizeof(int), sz_di);
     mp.getrf_id = (const int2*)put(getrf_id.data(), getrf_id.size() * sizeof(int2), sz_gi);
     mp.panel_id = (const int2*)put(panel_id.data(), panel_id.size() * sizeof(int2), sz_pi);
+    mp.cpair_dep = (const int2*)put(cpair_dep.data(), cpair_dep.size() * sizeof(int2), sz_cd);
+    mp.cpairs = pl->D.cpairs;
+    mp.ops = pl->D.ops;
     pl->remaining_init = (int*)put(remaining.data(), nid * sizeof(int), sz_ids);
     pl->done_init = (int*)put(done_init.data(), nid * sizeof(int), sz_ids);
     pl->pending_init = (int*)put(pending.data(), nid * sizeof(int), sz_ids);
@@ -835,7 +970,7 @@ void launch_mega(pangulu_sm100_plan* pl)
     MegaParams<T>& mp = pl->mp;
     if (mp.ntask == 0) return;
     Timer tm(K_MEGA);
-    const size_t smem = (size_t)g.max_smem_optin - 64;
+    const size_t smem = (size_t)g.max_smem_optin - 256;  // (static shared memory of the kernel: tickets, mbarriers)
     pl->mp.smem_bytes = smem;  // whole SM: the shared-memory GETRF variant sizes itself against this
     const int grid = g.sm_count;
     if (pl->nb <= 128)
@@ -1001,6 +1136,8 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "split_pairs")) return &g.opt.split_pairs;
     if (!strcmp(key, "executor")) return &g.opt.executor;
     if (!strcmp(key, "trace")) return &g.opt.trace;
+    if (!strcmp(key, "compact")) return &g.opt.compact;
+    if (!strcmp(key, "compact_threshold")) return &g.opt.compact_threshold;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)
@@ -1041,17 +1178,48 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     pangulu_sm100_plan* pl = new pangulu_sm100_plan();
     pl->nb = nb;
     pl->dev_buf = nullptr;
+    pl->reg.nb = nb;
     for (pangulu_uint64_t w = 0; w < nwave; ++w)
     {
         pl->wave_step.push_back(pl->P.steps.size());
-        append_tasks(pl->P, nb, tasks, waves[w], waves[w + 1], false);
+        append_tasks(pl->P, nb, tasks, waves[w], waves[w + 1], false, &pl->reg);
     }
     pl->wave_step.push_back(pl->P.steps.size());
     Program& P = pl->P;
-    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs);
+    // compact dense copies: allocate, zero, describe; tell every panel task which copy (if any) its block feeds
+    std::vector<DenseOp<T>> ops(pl->reg.entries.size());
+    if (!ops.empty())
+    {
+        DenseReg& R = pl->reg;
+        CK(cudaMalloc(&pl->dense_buf, R.dense_total * sizeof(T) + 256));
+        CK(cudaMemset(pl->dense_buf, 0, R.dense_total * sizeof(T) + 256));
+        CK(cudaMalloc(&pl->dense_meta, R.meta.size() * sizeof(u16) + 256));
+        CK(cudaMemcpy(pl->dense_meta, R.meta.data(), R.meta.size() * sizeof(u16), cudaMemcpyHostToDevice));
+        for (size_t i = 0; i < ops.size(); ++i)
+        {
+            const DenseReg::Entry& e = R.entries[i];
+            DenseOp<T>& o = ops[i];
+            memset(&o, 0, sizeof o);
+            o.dense = (T*)pl->dense_buf + e.dense_off;
+            o.list = (const u16*)pl->dense_meta + e.meta_off;
+            o.inv = o.list + e.cnt;
+            o.cnt = e.cnt;
+            o.ld = e.ld;
+            o.kmask = e.kmask;
+            memcpy(o.tile_start, e.tile_start, sizeof o.tile_start);
+            pl->op_val.push_back(e.slot->d_value);
+        }
+        for (size_t i = 0; i < P.panel.size(); ++i) P.panel[i].dense = R.find(P.panel_slot[i]);
+        std::vector<u16>().swap(R.meta);
+    }
+    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs), b4 = vbytes(P.cpairs), b5 = vbytes(ops);
     char* d = nullptr;
-    CK(cudaMalloc((void**)&d, b0 + b1 + b2 + b3 + 256));
+    CK(cudaMalloc((void**)&d, b0 + b1 + b2 + b3 + b4 + b5 + 256));
     pl->dev_buf = d;
+    if (!P.cpairs.empty()) CK(cudaMemcpy(d + b0 + b1 + b2 + b3, P.cpairs.data(), P.cpairs.size() * sizeof(CPair), cudaMemcpyHostToDevice));
+    if (!ops.empty()) CK(cudaMemcpy(d + b0 + b1 + b2 + b3 + b4, ops.data(), ops.size() * sizeof(DenseOp<T>), cudaMemcpyHostToDevice));
+    pl->D.cpairs = (CPair*)(d + b0 + b1 + b2 + b3);
+    pl->D.ops = ops.empty() ? nullptr : (DenseOp<T>*)(d + b0 + b1 + b2 + b3 + b4);
     if (!P.getrf.empty()) CK(cudaMemcpy(d, P.getrf.data(), P.getrf.size() * sizeof(GetrfTask<T>), cudaMemcpyHostToDevice));
     if (!P.panel.empty()) CK(cudaMemcpy(d + b0, P.panel.data(), P.panel.size() * sizeof(PanelTask<T>), cudaMemcpyHostToDevice));
     if (!P.dests.empty()) CK(cudaMemcpy(d + b0 + b1, P.dests.data(), P.dests.size() * sizeof(SsssmDest<T>), cudaMemcpyHostToDevice));
@@ -1066,6 +1234,8 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     std::vector<PanelTask<T>>().swap(P.panel);
     std::vector<SsssmDest<T>>().swap(P.dests);
     std::vector<SsssmPair<T>>().swap(P.pairs);
+    std::vector<CPair>().swap(P.cpairs);
+    std::vector<const pangulu_storage_slot_t*>().swap(P.panel_slot);
     return pl;
 }
 
@@ -1096,7 +1266,7 @@ long long pangulu_sm100_plan_trace(pangulu_sm100_plan* pl, unsigned long long* o
     for (long long i = 0; i < n && i < cap; ++i)
     {
         // kind in the low byte; for tile tasks the number of operand pairs above it
-        out[4 * i] = (unsigned long long)pl->host_tasks[i].kind | ((unsigned long long)(pl->host_tasks[i].kind == MEGA_TILE ? pl->host_tasks[i].c : 0) << 8);
+        out[4 * i] = (unsigned long long)pl->host_tasks[i].kind | ((unsigned long long)((pl->host_tasks[i].kind == MEGA_TILE || pl->host_tasks[i].kind == MEGA_CTILE) ? pl->host_tasks[i].c : 0) << 8);
         out[4 * i + 1] = tmp[3 * i];
         out[4 * i + 2] = tmp[3 * i + 1];
         out[4 * i + 3] = tmp[3 * i + 2];
@@ -1110,6 +1280,8 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
     if (pl->dev_buf) CK(cudaFree(pl->dev_buf));
     if (pl->mega_buf) CK(cudaFree(pl->mega_buf));
     if (pl->push_buf) CK(cudaFree(pl->push_buf));
+    if (pl->dense_buf) CK(cudaFree(pl->dense_buf));
+    if (pl->dense_meta) CK(cudaFree(pl->dense_meta));
     delete pl;
 }
 

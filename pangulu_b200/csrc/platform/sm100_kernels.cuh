@@ -27,6 +27,15 @@ __device__ __forceinline__ void red_sub(float* a, float v) { atomicAdd(a, -v); }
 __device__ __forceinline__ void red_sub(pangulu_sm100_c64* a, pangulu_sm100_c64 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
 __device__ __forceinline__ void red_sub(pangulu_sm100_c32* a, pangulu_sm100_c32 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
 
+__device__ inline void vadd(double& x, double a) { x += a; }
+__device__ inline void vadd(float& x, float a) { x += a; }
+__device__ inline void vadd(pangulu_sm100_c64& x, pangulu_sm100_c64 a) { x.re += a.re; x.im += a.im; }
+__device__ inline void vadd(pangulu_sm100_c32& x, pangulu_sm100_c32 a) { x.re += a.re; x.im += a.im; }
+
+}  // namespace psm
+#include "sm100_compact.cuh"
+namespace psm {
+
 // ------------------------------------------------------------------------------------------------
 // SSSSM, sparse path.  grid = (#destinations x column groups); one warp owns one column j of the
 // destination and applies EVERY operand pair queued for that destination (ascending elimination
@@ -155,8 +164,9 @@ ssssm_sparse_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmP
 // elements of the next sweep are loaded ahead.
 //   smem = warps * nb * sizeof(T)
 // ------------------------------------------------------------------------------------------------
+// dop (optional): compact dense copy of the block (sm100_compact.cuh); the finished row / column is written into it too
 template <class T>
-__device__ __forceinline__ void panel_solve_line(int nb, const PanelTask<T>& P, int rc, T* x)
+__device__ __forceinline__ void panel_solve_line(int nb, const PanelTask<T>& P, int rc, T* x, const DenseOp<T>* dop = nullptr)
 {
     const int lane = threadIdx.x % PSM_WARP;
     const Blk<T> B = P.b, Dg = P.diag;
@@ -222,12 +232,21 @@ __device__ __forceinline__ void panel_solve_line(int nb, const PanelTask<T>& P, 
         for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[e] = x[bidx[e]];
     else
         for (u32 e = b0 + lane; e < b1; e += PSM_WARP) B.val[B.rmap[e]] = x[bidx[e]];
+    if (dop)
+    {
+        const DenseOp<T> Dn = *dop;
+        const int cidx = Dn.inv[rc];  // compact column (GESSM: block of the U panel) / compact row (TSTRF: block of the L panel)
+        if (gessm)
+            for (u32 e = b0 + lane; e < b1; e += PSM_WARP) dense_store_b(Dn, bidx[e], cidx, x[bidx[e]]);
+        else
+            for (u32 e = b0 + lane; e < b1; e += PSM_WARP) Dn.dense[(size_t)bidx[e] * Dn.ld + cidx] = x[bidx[e]];
+    }
     __syncwarp();
 }
 
 template <class T, int WARPS>
 __global__ void __launch_bounds__(WARPS * PSM_WARP)
-panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_per_task)
+panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_per_task, const DenseOp<T>* __restrict__ ops)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* x_all = reinterpret_cast<T*>(smem_raw);
@@ -236,7 +255,7 @@ panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_pe
     const int rc = (blockIdx.x % groups_per_task) * WARPS + warp;
     if (rc >= nb) return;
     const PanelTask<T> P = tasks[t];
-    panel_solve_line<T>(nb, P, rc, x_all + (size_t)warp * nb);
+    panel_solve_line<T>(nb, P, rc, x_all + (size_t)warp * nb, (ops && P.dense >= 0) ? ops + P.dense : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -542,11 +561,6 @@ __global__ void spmv_kernel(int nb, Blk<T> A, const T* __restrict__ x, T* __rest
     const T xv = x[col];
     for (u32 e = col_begin(A.ptr, col) + lane; e < A.ptr[col + 1]; e += PSM_WARP) atomic_sub(&y[A.idx[e]], vmul(A.val[e], xv));
 }
-
-__device__ inline void vadd(double& x, double a) { x += a; }
-__device__ inline void vadd(float& x, float a) { x += a; }
-__device__ inline void vadd(pangulu_sm100_c64& x, pangulu_sm100_c64 a) { x.re += a.re; x.im += a.im; }
-__device__ inline void vadd(pangulu_sm100_c32& x, pangulu_sm100_c32 a) { x.re += a.re; x.im += a.im; }
 
 template <class T> __device__ inline T warp_sum(T s)
 {
@@ -1086,7 +1100,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 // ================================================================================================
 struct MegaTask { int kind, a, b, c; };
 template <class T> struct MegaPush { T* peer_val; int* peer_flag; };
-enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5 };
+enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6 };
 
 template <class T>
 struct MegaParams
@@ -1096,6 +1110,9 @@ struct MegaParams
     const SsssmDest<T>* dests;
     const SsssmPair<T>* pairs;
     const int2* pair_dep;   // per pair: sync ids of A and B
+    const CPair* cpairs;    // operand pairs of the compact-tile destinations (indices into ops)
+    const int2* cpair_dep;  // per compact pair: sync ids of A and B
+    const DenseOp<T>* ops;  // compact dense copies of operand blocks
     const int* dest_id;     // per destination descriptor: sync id of the destination
     const GetrfTask<T>* getrf;
     const int2* getrf_id;   // sync ids of the lower and the upper half
@@ -1194,6 +1211,7 @@ mega_kernel(const MegaParams<T> P)
     __shared__ int s_last;
     const int tid = threadIdx.x, warp = tid / PSM_WARP;
     const int nb = P.nb;
+    CtState ct_state;
     for (;;)
     {
         if (tid == 0) s_ticket = atomicAdd(P.counter, 1);
@@ -1206,18 +1224,24 @@ mega_kernel(const MegaParams<T> P)
         {
         case MEGA_TILE:
         case MEGA_SPARSE:
+        case MEGA_CTILE:
         {
             const SsssmDest<T> D = P.dests[mt.a];
             if (tid == 0)
+            {
+                const int2* deps = mt.kind == MEGA_CTILE ? P.cpair_dep : P.pair_dep;
                 for (u32 p = D.pair_begin; p < D.pair_end; ++p)
                 {
-                    const int2 dep = P.pair_dep[p];
+                    const int2 dep = deps[p];
                     spin_until_set(P.done + dep.x, P.multi);
                     spin_until_set(P.done + dep.y, P.multi);
                 }
+            }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
-            if (mt.kind == MEGA_TILE)
+            if (mt.kind == MEGA_CTILE)
+                ssssm_ctile_cta<T, ct_traits<T>::TN, ct_traits<T>::STAGES>(smem_raw, nb, D, P.cpairs, P.ops, mt.b * ct_traits<T>::TN, ct_state);
+            else if (mt.kind == MEGA_TILE)
                 ssssm_tile2_cta<T, TM>(smem_raw, nb, D, P.pairs, mt.b * PSM_TILE_N, true);
             else
             {
@@ -1294,7 +1318,8 @@ mega_kernel(const MegaParams<T> P)
                 }
                 __syncthreads();
             }
-            for (int rc = mt.b + warp; rc < mt.b + 64 && rc < nb; rc += 16) panel_solve_line<T>(nb, Q2, rc, x);
+            const DenseOp<T>* dop = (P.ops && Q.dense >= 0) ? P.ops + Q.dense : nullptr;
+            for (int rc = mt.b + warp; rc < mt.b + 64 && rc < nb; rc += 16) panel_solve_line<T>(nb, Q2, rc, x, dop);
             __threadfence();
             __syncthreads();
             if (tid == 0)

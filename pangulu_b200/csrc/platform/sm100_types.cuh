@@ -115,7 +115,8 @@ struct Blk
 template <class T> struct GetrfTask { Blk<T> lower, upper; };
 // TSTRF: b = strictly-lower block (uses its CSR mirror), diag = UPPER half of the diagonal block
 // GESSM: b = upper block (CSC), diag = LOWER half of the diagonal block
-template <class T> struct PanelTask { Blk<T> b, diag; int kind; int pad; };
+// dense: index of the block's compact dense copy (sm100_compact.cuh) or -1
+template <class T> struct PanelTask { Blk<T> b, diag; int kind; int dense; };
 // SSSSM: destination (c = the block, or the LOWER half when the destination is a diagonal block;
 // u = UPPER half or null) and the range of (A,B) operand pairs applied to it
 // read-only CSC operand of an SSSSM pair

@@ -6,7 +6,7 @@ from pangulu_b200 import PanguLU, matrices, _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=48); ap.add_argument("--nb", type=int, default=256)
 ap.add_argument("--schedule", type=int, default=2); ap.add_argument("--lookahead", type=int, default=6)
-ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--out", default="gpurun_out/trace.npy")
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--out", default="")
 a = ap.parse_args()
 L = _lib.load("r64")
 L.pangulu_sm100_set_option(b"trace", 1); L.pangulu_sm100_set_option(b"executor", 1)
@@ -17,19 +17,23 @@ s.gstrf(); s.reset_values(True); t = s.gstrf()
 n = L.pangulu_sm100_driver_trace(s._h, None, 0)
 buf = np.zeros((n, 4), dtype=np.uint64)
 L.pangulu_sm100_driver_trace(s._h, buf.ctypes.data, n)
-os.makedirs(os.path.dirname(a.out), exist_ok=True)
-np.save(a.out, buf)
+if a.out:
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    np.save(a.out, buf)
 kind = (buf[:, 0] & 0xff).astype(int); npairs = (buf[:, 0] >> 8).astype(int); t0 = buf[:, 1].min()
 fetch, start, end = [(buf[:, i] - t0).astype(np.int64) / 1e3 for i in (1, 2, 3)]
-names = ["tile", "sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel"]
+names = ["tile", "sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel", "ctile"]
 print(f"gstrf {t*1e3:.1f} ms, {n} tasks, span {end.max()/1e3:.1f} ms")
-for k in range(6):
+for k in range(7):
     m = kind == k
     if m.any():
         run, wait = end[m] - start[m], start[m] - fetch[m]
         print(f"{names[k]:12s} n={m.sum():7d} run total {run.sum()/1e3:9.1f} ms mean {run.mean():8.1f} us max {run.max():9.1f} | wait total {wait.sum()/1e3:9.1f} ms mean {wait.mean():8.1f} us")
-m = kind == 0
-print("tile tasks: pairs total", npairs[m].sum(), "mean", npairs[m].mean().round(2), "max", npairs[m].max(), "| us per pair-tile", ((end[m]-start[m]).sum()/npairs[m].sum()).round(2))
+print(f"flop {s.info('flop'):.4e}  -> {s.info('flop')/t/1e9:.1f} GFLOP/s")
+for k in (0, 6):
+    m = kind == k
+    if m.any():
+        print(names[k], "tasks: pairs total", npairs[m].sum(), "mean", npairs[m].mean().round(2), "max", npairs[m].max(), "| us per pair-tile", ((end[m]-start[m]).sum()/npairs[m].sum()).round(2))
 busy = (end - start).sum() / 1e3; waiting = (start - fetch).sum() / 1e3
 print(f"sum over CTAs: busy {busy:.1f} ms, waiting {waiting:.1f} ms, capacity 148 x span = {148*end.max()/1e3:.1f} ms")
 # critical chain through getrf tasks

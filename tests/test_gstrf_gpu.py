@@ -140,3 +140,46 @@ def test_refactor_after_reset():
             assert rel_err(a, b) <= 1e-13
     finally:
         s.finalize()
+
+
+@pytest.mark.parametrize("executor", [1, 0], ids=["persistent", "per-wave-launches"])
+@pytest.mark.parametrize("vtype,threshold", [("r64", 0), ("r64", 10), ("r32", 0), ("cr64", 0), ("cr32", 0)])
+def test_gstrf_compact_dense_path(vtype, threshold, executor):
+    """SSSSM on row/column-compacted dense operand copies (sm100_compact.cuh): with threshold 0 EVERY update of the
+    resident plan goes through the compact tile kernel (DMMA for R64, FMA tiles otherwise), and the panel solves
+    maintain the compact copies.  Same gates as the other paths."""
+    dtype = _lib.VALUE_DTYPES[vtype]
+    nb = 64 if vtype == "r64" else 32
+    if np.dtype(dtype).kind == "c":
+        A = matrices.circuit_like(700, seed=5, dmax=20, dtype=dtype)
+    else:
+        A = (matrices.stencil27(9) if threshold == 0 else matrices.poisson3d(14)).astype(dtype)
+    n = A.shape[0]
+    want, _, _ = _expected(A, nb, vtype)
+    L = _lib.load(vtype)
+    L.pangulu_sm100_set_option(b"compact", 1)
+    L.pangulu_sm100_set_option(b"compact_threshold", threshold)
+    L.pangulu_sm100_set_option(b"executor", executor)
+    s = PanguLU(A, nb=nb, mode=1)
+    try:
+        L.pangulu_sm100_stats_reset()
+        s.gstrf()
+        s.download()
+        if executor == 0:
+            assert L.pangulu_sm100_stats_launches(7) > 0, "compact tile kernel did not run"
+        tol = TOL[vtype] * (10 if "32" in vtype else 1)
+        worst = max(rel_err(g.value, w.value) for g, w in zip(s.blocks(copy=True), want))
+        assert worst <= tol, f"L/U values differ by {worst:.3e}"
+        s.reset_values(True)   # the compact copies are rewritten by the second factorisation
+        s.gstrf()
+        s.download()
+        worst = max(rel_err(g.value, w.value) for g, w in zip(s.blocks(copy=True), want))
+        assert worst <= tol, f"second run: L/U values differ by {worst:.3e}"
+        b = (A @ np.ones(n, dtype=dtype)).astype(dtype)
+        x = s.gstrs(b)
+        resid = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
+        assert resid <= (1e-4 if "32" in vtype else 1e-12)
+    finally:
+        L.pangulu_sm100_set_option(b"compact_threshold", 10)
+        L.pangulu_sm100_set_option(b"executor", 1)
+        s.finalize()
