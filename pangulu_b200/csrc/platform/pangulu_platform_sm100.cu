@@ -46,7 +46,7 @@ typedef calculate_type T;
     } while (0)
 #define CK_LAST() CK(cudaGetLastError())
 
-enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_MEGA = 6, K_SSSSM_CTILE = 7, K_NCLASS = 8 };
+enum KClass { K_GETRF = 0, K_TSTRF = 1, K_GESSM = 2, K_SSSSM_SPARSE = 3, K_SSSSM_TILE = 4, K_AUX = 5, K_MEGA = 6, K_SSSSM_CTILE = 7, K_CPANEL = 8, K_NCLASS = 9 };
 enum { K_GETRF_SMEM = 100, K_GETRF_DENSE = 101 };  // step kinds only; accounted under K_GETRF
 
 struct Options
@@ -62,6 +62,7 @@ struct Options
     long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
     long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
     long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path
+    long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -81,8 +82,8 @@ struct Ctx
     cudaStream_t stream = nullptr;
     Options opt;
     std::vector<Slab> slabs;
-    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
-    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long launches[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    double ms[K_NCLASS] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int max_smem_optin = 0;
     int sm_count = 0;
@@ -192,6 +193,7 @@ struct Step
     size_t off;        // first descriptor (index into the class's array)
     size_t count;      // descriptors (GETRF tasks / panel tasks / SSSSM destinations)
     size_t smem = 0;   // dynamic shared memory of the launch where it depends on the batch
+    size_t aux_off = 0, aux_count = 0;  // compact-tile steps: range of tile tasks (Program::ctasks)
 };
 struct Download { void* h; const void* d; size_t bytes; };
 
@@ -203,6 +205,10 @@ struct Program
     std::vector<SsssmDest<T>> dests;
     std::vector<SsssmPair<T>> pairs;
     std::vector<CPair> cpairs;        // operand pairs of the compact-tile destinations
+    std::vector<CTileTask> ctasks;    // (destination, column range) tiles of the compact-tile destinations
+    std::vector<CPanelTask> cptasks;  // (panel task, dense diagonal, first compact row/column) slices of the compact panel solves
+    std::vector<int> getrf_dd;        // per GETRF task: dense triangular copies to refresh (index) or -1
+    std::vector<const pangulu_storage_slot_t*> getrf_slot;  // lower-half slot of each GETRF task
     std::vector<Step> steps;
     std::vector<Download> downloads;  // referenced by steps of kind -1 (off/count)
 };
@@ -215,6 +221,10 @@ struct DevProgram
     SsssmPair<T>* pairs = nullptr;
     CPair* cpairs = nullptr;
     DenseOp<T>* ops = nullptr;
+    CTileTask* ctasks = nullptr;
+    CPanelTask* cptasks = nullptr;
+    DiagDense<T>* dds = nullptr;
+    int* getrf_dd = nullptr;
 };
 
 // Registry of the compact dense operand copies of one plan (sm100_compact.cuh): which blocks have one, their row /
@@ -226,8 +236,7 @@ struct DenseReg
         const pangulu_storage_slot_t* slot;
         u32 cnt, ld, kmask;
         size_t dense_off, dense_len;  // in values
-        size_t meta_off;              // in u16: list[cnt] then inv[nb]
-        u16 tile_start[18];
+        size_t meta_off;              // in u16: list[cnt], inv[nb], then (B operands) pre[nb+1]
     };
     int nb = 0;
     std::vector<Entry> entries;
@@ -273,13 +282,6 @@ struct DenseReg
             e.cnt = (u32)list.size();
             e.ld = PSM_CT_BLD;
             e.dense_len = (size_t)(nb / PSM_CT_KC) * e.cnt * PSM_CT_BLD;
-            u32 run = 0;
-            size_t li = 0;
-            for (int t = 0; t <= nb / 16; ++t)
-            {
-                while (li < list.size() && list[li] < 16 * t) { ++li; ++run; }
-                e.tile_start[t] = (u16)run;
-            }
         }
         e.kmask = kmask;
         e.dense_off = dense_total;
@@ -287,6 +289,15 @@ struct DenseReg
         e.meta_off = meta.size();
         meta.insert(meta.end(), list.begin(), list.end());
         meta.insert(meta.end(), inv.begin(), inv.end());
+        if (as_b)
+        {
+            u16 run = 0;
+            for (int c = 0; c <= nb; ++c)
+            {
+                meta.push_back(run);
+                if (c < nb && inv[c] != 0xffff) ++run;
+            }
+        }
         const int id = (int)entries.size();
         entries.push_back(e);
         index.emplace(s, id);
@@ -343,6 +354,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 return fa != fb ? fa < fb : cls[a] < cls[b];
             });
             std::vector<SsssmDest<T>> by_cls[3];
+            std::vector<pangulu_storage_slot_t*> cslot;  // destination slots of by_cls[2]
             const void* cur = nullptr;
             int cur_cls = -1;
             for (size_t k : order)
@@ -372,6 +384,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                     D.pair_begin = (u32)(cur_cls == 2 ? P.cpairs.size() : P.pairs.size());
                     D.pair_end = D.pair_begin;
                     by_cls[cur_cls].push_back(D);
+                    if (cur_cls == 2) cslot.push_back(d);
                 }
                 if (cur_cls == 2)
                 {
@@ -421,7 +434,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 if (by_cls[c].empty()) continue;
                 // per-wave launches: heaviest destinations first (the grid is consumed in order, this trims the tail);
                 // persistent executor: keep the caller's priority order
-                if (g.opt.executor != 1)
+                if (g.opt.executor != 1 && c != 2)  // (class 2 keeps its order: cslot runs parallel to it)
                     std::stable_sort(by_cls[c].begin(), by_cls[c].end(), [](const SsssmDest<T>& x, const SsssmDest<T>& y) {
                         return (x.pair_end - x.pair_begin) > (y.pair_end - y.pair_begin);
                     });
@@ -429,6 +442,56 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 st.kind = c == 0 ? K_SSSSM_TILE : c == 1 ? K_SSSSM_SPARSE : K_SSSSM_CTILE;
                 st.off = P.dests.size();
                 st.count = by_cls[c].size();
+                if (c == 2)
+                {
+                    // cut every destination into column ranges in which neither the destination nor any of its B operands has
+                    // more than TN non-empty columns (a B operand may have columns the destination lacks: their products
+                    // are structurally empty)
+                    constexpr int TN = ct_traits<T>::TN;
+                    st.aux_off = P.ctasks.size();
+                    std::vector<u16> cpre((size_t)nb + 1);
+                    for (size_t di = 0; di < by_cls[2].size(); ++di)
+                    {
+                        const SsssmDest<T>& D2 = by_cls[2][di];
+                        pangulu_storage_slot_t* ds = cslot[di];
+                        pangulu_storage_slot_t *lo = ds, *up = nullptr;
+                        if (ds->brow_pos == ds->bcol_pos) diag_halves(ds, lo, up);
+                        u16 run = 0;
+                        for (int cc = 0; cc <= nb; ++cc)
+                        {
+                            cpre[cc] = run;
+                            if (cc < nb)
+                            {
+                                bool ne = lo->columnpointer[cc + 1] > (cc ? lo->columnpointer[cc] : 0u);
+                                if (up) ne = ne || up->columnpointer[cc + 1] > (cc ? up->columnpointer[cc] : 0u);
+                                run += ne;
+                            }
+                        }
+                        int s0 = 0;
+                        while (s0 < nb && cpre[nb] > cpre[s0])
+                        {
+                            // largest end such that every count stays <= TN
+                            int e = nb;
+                            auto limit = [&](const u16* pre) {
+                                // first column c with pre[c+1] - pre[s0] > TN  ->  range must end at c
+                                const int target = pre[s0] + TN;
+                                if (pre[nb] <= target) return;
+                                int a = s0, b = nb;  // smallest c with pre[c] > target
+                                while (a < b) { const int m2 = (a + b) >> 1; if (pre[m2] > target) b = m2; else a = m2 + 1; }
+                                e = std::min(e, a - 1);
+                            };
+                            limit(cpre.data());
+                            for (u32 pp = D2.pair_begin; pp < D2.pair_end; ++pp)
+                            {
+                                const DenseReg::Entry& eb = reg->entries[P.cpairs[pp].b];
+                                limit(reg->meta.data() + eb.meta_off + eb.cnt + nb);
+                            }
+                            if (cpre[e] > cpre[s0]) P.ctasks.push_back({(int)(st.off + di), s0, e});
+                            s0 = e;
+                        }
+                    }
+                    st.aux_count = P.ctasks.size() - st.aux_off;
+                }
                 P.dests.insert(P.dests.end(), by_cls[c].begin(), by_cls[c].end());
                 P.steps.push_back(st);
             }
@@ -439,6 +502,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             size_t j = i;
             // diagonal blocks that fit in shared memory (values + pattern of both halves) take the staged kernel
             std::vector<GetrfTask<T>> fit, big;
+            std::vector<const pangulu_storage_slot_t*> fit_slot, big_slot;
             size_t fit_smem = 0;
             Step dl; dl.kind = -1; dl.off = P.downloads.size(); dl.count = 0;
             while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_GETRF)
@@ -452,8 +516,8 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 const size_t need = getrf_smem_bytes(nb, nl, nu);
                 // getrf_mode: 0 auto, 1 never stage in shared memory, 2 never promote to dense, 3 always dense (nb <= 256)
                 const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256;
-                if (!want_dense && need + 256 <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); }
-                else big.push_back(G);
+                if (!want_dense && need + 512 <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); fit_slot.push_back(lo); }
+                else { big.push_back(G); big_slot.push_back(lo); }
                 if (eager_download)
                 {
                     P.downloads.push_back({lo->value, lo->d_value, sizeof(T) * nl});
@@ -466,6 +530,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             {
                 Step st; st.kind = K_GETRF_SMEM; st.off = P.getrf.size(); st.count = fit.size(); st.smem = fit_smem;
                 P.getrf.insert(P.getrf.end(), fit.begin(), fit.end());
+                P.getrf_slot.insert(P.getrf_slot.end(), fit_slot.begin(), fit_slot.end());
                 P.steps.push_back(st);
             }
             if (!big.empty())
@@ -473,6 +538,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 // too full for shared memory: dense-promoted blocked LU (nb <= 256), else the global-memory sparse kernel
                 Step st; st.kind = (nb <= 256 && g.opt.getrf_mode != 2) ? (int)K_GETRF_DENSE : (int)K_GETRF; st.off = P.getrf.size(); st.count = big.size(); st.smem = 0;
                 P.getrf.insert(P.getrf.end(), big.begin(), big.end());
+                P.getrf_slot.insert(P.getrf_slot.end(), big_slot.begin(), big_slot.end());
                 P.steps.push_back(st);
             }
             if (dl.count) P.steps.push_back(dl);
@@ -513,6 +579,12 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 ++j;
             }
             P.steps.push_back(st);
+            if (reg)
+            {
+                // filled by the plan's post-pass: the panel tasks of this run that take the compact dense path
+                Step cs; cs.kind = K_CPANEL; cs.off = st.off; cs.count = 0;
+                P.steps.push_back(cs);
+            }
             if (dl.count) P.steps.push_back(dl);
             i = j;
         }
@@ -630,17 +702,34 @@ void launch_ssssm_tile(int nb, const SsssmDest<T>* d, const SsssmPair<T>* p, siz
     g.launches[K_SSSSM_TILE]++;
 }
 
-void launch_ssssm_ctile(int nb, const SsssmDest<T>* d, const CPair* cp, const DenseOp<T>* ops, size_t ndest)
+void launch_ssssm_ctile(int nb, const SsssmDest<T>* d, const CPair* cp, const DenseOp<T>* ops, const CTileTask* ctasks, size_t ntile)
 {
-    if (!ndest) return;
+    if (!ntile) return;
     Timer tm(K_SSSSM_CTILE);
     constexpr int TN = ct_traits<T>::TN;
-    const int tiles = (nb + TN - 1) / TN;
     const size_t smem = CtLayout<T, TN, ct_traits<T>::STAGES>::total;
     set_smem(ssssm_ctile_kernel<T>, smem);
-    ssssm_ctile_kernel<T><<<(unsigned)(ndest * tiles), 512, smem, g.stream>>>(nb, d, cp, ops, tiles);
+    ssssm_ctile_kernel<T><<<(unsigned)ntile, 512, smem, g.stream>>>(nb, d, cp, ops, ctasks);
     CK_LAST();
     g.launches[K_SSSSM_CTILE]++;
+}
+
+void launch_cpanel(int nb, const PanelTask<T>* tasks, const CPanelTask* cpt, size_t n, const DenseOp<T>* ops, const DiagDense<T>* dds)
+{
+    if (!n) return;
+    Timer tm(K_CPANEL);
+    const size_t smem = CpLayout<T>::total;
+    set_smem(panel_compact_kernel<T>, smem);
+    panel_compact_kernel<T><<<(unsigned)n, 512, smem, g.stream>>>(nb, tasks, cpt, ops, dds);
+    CK_LAST();
+    g.launches[K_CPANEL]++;
+}
+void launch_diag_densify(int nb, const GetrfTask<T>* t, const int* getrf_dd, const DiagDense<T>* dds, size_t n)
+{
+    if (!n || !dds) return;
+    diag_densify_kernel<T><<<(unsigned)n, 256, 0, g.stream>>>(nb, t, getrf_dd, dds);
+    CK_LAST();
+    g.launches[K_AUX]++;
 }
 
 template <int WARPS> void launch_panel_w(int nb, const PanelTask<T>* t, size_t n, const DenseOp<T>* ops)
@@ -719,10 +808,11 @@ void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t 
         {
         case K_SSSSM_SPARSE: launch_ssssm_sparse(nb, D.dests + st.off, D.pairs, st.count); break;
         case K_SSSSM_TILE: launch_ssssm_tile(nb, D.dests + st.off, D.pairs, st.count); break;
-        case K_SSSSM_CTILE: launch_ssssm_ctile(nb, D.dests + st.off, D.cpairs, D.ops, st.count); break;
-        case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); break;
-        case K_GETRF_SMEM: launch_getrf_smem(nb, D.getrf + st.off, st.count, st.smem); break;
-        case K_GETRF_DENSE: launch_getrf_dense(nb, D.getrf + st.off, st.count); break;
+        case K_SSSSM_CTILE: launch_ssssm_ctile(nb, D.dests, D.cpairs, D.ops, D.ctasks + st.aux_off, st.aux_count); break;
+        case K_GETRF: launch_getrf(nb, D.getrf + st.off, st.count); launch_diag_densify(nb, D.getrf + st.off, D.getrf_dd ? D.getrf_dd + st.off : nullptr, D.dds, st.count); break;
+        case K_GETRF_SMEM: launch_getrf_smem(nb, D.getrf + st.off, st.count, st.smem); launch_diag_densify(nb, D.getrf + st.off, D.getrf_dd ? D.getrf_dd + st.off : nullptr, D.dds, st.count); break;
+        case K_GETRF_DENSE: launch_getrf_dense(nb, D.getrf + st.off, st.count); launch_diag_densify(nb, D.getrf + st.off, D.getrf_dd ? D.getrf_dd + st.off : nullptr, D.dds, st.count); break;
+        case K_CPANEL: launch_cpanel(nb, D.panel, D.cptasks + st.aux_off, st.aux_count, D.ops, D.dds); break;
         case K_TSTRF: launch_panel(nb, D.panel + st.off, st.count, D.ops); break;
         case -1:
             for (size_t k = st.off; k < st.off + st.count; ++k)
@@ -735,6 +825,8 @@ void run_steps(int nb, const Program& P, const DevProgram& D, size_t s0, size_t 
 }
 
 template <class V> size_t vbytes(const V& v) { return (v.size() * sizeof(typename V::value_type) + 255) & ~(size_t)255; }
+
+inline u32 R_cnt(const DenseReg& R, int op) { return R.entries[op].cnt; }
 
 // one-shot execution of a task array (the hybrid_batched / getrf / tstrf / ... entry points)
 void execute_tasks(int nb, size_t ntask, const pangulu_task_t* tasks)
@@ -788,6 +880,7 @@ struct pangulu_sm100_plan
     void* dense_buf = nullptr;   // values (zero-filled once; structural zeros stay zero)
     void* dense_meta = nullptr;  // row / column lists and inverse maps
     std::vector<const void*> op_val;  // per compact copy: device value array of the block it mirrors (sync id key)
+    void* diag_dense_buf = nullptr;   // dense triangular copies of diagonal blocks (compact panel path)
     // persistent executor
     bool mega = false;
     void* mega_buf = nullptr;
@@ -842,7 +935,6 @@ void build_mega(pangulu_sm100_plan* pl)
         touch(cpair_dep[p].y);
     }
     const int tiles = (nb + PSM_TILE_N - 1) / PSM_TILE_N;
-    const int ctiles = (nb + ct_traits<T>::TN - 1) / ct_traits<T>::TN;
     const int sgroup = 64, sgroups = (nb + sgroup - 1) / sgroup;
     for (const Step& st : P.steps)
     {
@@ -857,10 +949,7 @@ void build_mega(pangulu_sm100_plan* pl)
                 touch(id);
                 dest_id[d] = id;
                 if (st.kind == K_SSSSM_CTILE)
-                {
-                    for (int t = 0; t < ctiles; ++t) tasks.push_back({MEGA_CTILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
-                    remaining[id] += ctiles;
-                }
+                    ;  // tile tasks below
                 else if (st.kind == K_SSSSM_TILE)
                 {
                     for (int t = 0; t < tiles; ++t) tasks.push_back({MEGA_TILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
@@ -872,6 +961,13 @@ void build_mega(pangulu_sm100_plan* pl)
                     remaining[id] += sgroups;
                 }
             }
+            if (st.kind == K_SSSSM_CTILE)
+                for (size_t c = st.aux_off; c < st.aux_off + st.aux_count; ++c)
+                {
+                    const CTileTask& ct = P.ctasks[c];
+                    tasks.push_back({MEGA_CTILE, ct.dest, ct.clo | (ct.chi << 16), (int)(P.dests[ct.dest].pair_end - P.dests[ct.dest].pair_begin)});
+                    remaining[dest_id[ct.dest]] += 1;
+                }
             break;
         case K_GETRF:
         case K_GETRF_SMEM:
@@ -887,6 +983,7 @@ void build_mega(pangulu_sm100_plan* pl)
             }
             break;
         case K_TSTRF:
+        case K_CPANEL:
             for (size_t ti = st.off; ti < st.off + st.count; ++ti)
             {
                 const int ib = id_of(P.panel[ti].b.val), idg = id_of(P.panel[ti].diag.val);
@@ -894,8 +991,15 @@ void build_mega(pangulu_sm100_plan* pl)
                 touch(idg);
                 panel_id[ti] = make_int2(ib, idg);
                 produced[ib] = 1;
-                for (int r0 = 0; r0 < nb; r0 += 64) { tasks.push_back({MEGA_PANEL, (int)ti, r0, 0}); pending[ib]++; }
+                if (st.kind == K_TSTRF)
+                    for (int r0 = 0; r0 < nb; r0 += 64) { tasks.push_back({MEGA_PANEL, (int)ti, r0, 0}); pending[ib]++; }
             }
+            if (st.kind == K_CPANEL)
+                for (size_t c = st.aux_off; c < st.aux_off + st.aux_count; ++c)
+                {
+                    tasks.push_back({MEGA_CPANEL, (int)c, 0, 0});
+                    pending[panel_id[P.cptasks[c].panel].x]++;
+                }
             break;
         default: break;  // downloads are not part of a plan
         }
@@ -931,6 +1035,9 @@ void build_mega(pangulu_sm100_plan* pl)
     mp.cpair_dep = (const int2*)put(cpair_dep.data(), cpair_dep.size() * sizeof(int2), sz_cd);
     mp.cpairs = pl->D.cpairs;
     mp.ops = pl->D.ops;
+    mp.cptasks = pl->D.cptasks;
+    mp.dds = pl->D.dds;
+    mp.getrf_dd = pl->D.getrf_dd;
     pl->remaining_init = (int*)put(remaining.data(), nid * sizeof(int), sz_ids);
     pl->done_init = (int*)put(done_init.data(), nid * sizeof(int), sz_ids);
     pl->pending_init = (int*)put(pending.data(), nid * sizeof(int), sz_ids);
@@ -970,7 +1077,7 @@ void launch_mega(pangulu_sm100_plan* pl)
     MegaParams<T>& mp = pl->mp;
     if (mp.ntask == 0) return;
     Timer tm(K_MEGA);
-    const size_t smem = (size_t)g.max_smem_optin - 256;  // (static shared memory of the kernel: tickets, mbarriers)
+    const size_t smem = (size_t)g.max_smem_optin - 512;  // (static shared memory of the kernel: tickets, mbarriers)
     pl->mp.smem_bytes = smem;  // whole SM: the shared-memory GETRF variant sizes itself against this
     const int grid = g.sm_count;
     if (pl->nb <= 128)
@@ -1138,6 +1245,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "trace")) return &g.opt.trace;
     if (!strcmp(key, "compact")) return &g.opt.compact;
     if (!strcmp(key, "compact_threshold")) return &g.opt.compact_threshold;
+    if (!strcmp(key, "cpanel")) return &g.opt.cpanel;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)
@@ -1206,20 +1314,131 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             o.cnt = e.cnt;
             o.ld = e.ld;
             o.kmask = e.kmask;
-            memcpy(o.tile_start, e.tile_start, sizeof o.tile_start);
+            o.pre = o.inv + pl->reg.nb;
             pl->op_val.push_back(e.slot->d_value);
         }
         for (size_t i = 0; i < P.panel.size(); ++i) P.panel[i].dense = R.find(P.panel_slot[i]);
-        std::vector<u16>().swap(R.meta);
     }
-    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs), b4 = vbytes(P.cpairs), b5 = vbytes(ops);
+    // compact panel path: panel tasks whose block has a compact copy and whose diagonal block is factored on this rank
+    std::vector<DiagDense<T>> dds;
+    P.getrf_dd.assign(P.getrf.size(), -1);
+    if (!ops.empty() && g.opt.cpanel != 0 && sizeof(T) <= 8 && nb % 16 == 0 && nb <= 256)
+    {
+        struct DiagNeed { bool u = false, lt = false; int index = -1; };
+        std::unordered_map<const pangulu_storage_slot_t*, DiagNeed> need;  // keyed by the lower-half slot
+        std::vector<const pangulu_storage_slot_t*> diag_of(P.panel.size(), nullptr);
+        std::vector<char> compact(P.panel.size(), 0);
+        // the diagonal halves of a panel task were resolved when the task was appended; find the lower-half slot again
+        // through the value pointer of the task's diagonal operand
+        std::unordered_map<const void*, const pangulu_storage_slot_t*> lower_of_val;
+        for (const pangulu_storage_slot_t* lo : P.getrf_slot)
+        {
+            lower_of_val.emplace(lo->d_value, lo);
+            lower_of_val.emplace(lo->related_block->d_value, lo);
+        }
+        for (size_t i = 0; i < P.panel.size(); ++i)
+        {
+            if (P.panel[i].dense < 0) continue;
+            auto it = lower_of_val.find(P.panel[i].diag.val);
+            if (it == lower_of_val.end()) continue;  // diagonal block factored by another rank
+            compact[i] = 1;
+            diag_of[i] = it->second;
+            DiagNeed& dn = need[it->second];
+            if (P.panel[i].kind == PANGULU_TASK_GESSM) dn.lt = true; else dn.u = true;
+        }
+        const size_t tri = (size_t)(nb / 16) * nb * PSM_CT_BLD;  // values per triangular copy
+        size_t total = 0;
+        for (size_t gi = 0; gi < P.getrf_slot.size(); ++gi)
+        {
+            auto it = need.find(P.getrf_slot[gi]);
+            if (it == need.end()) continue;
+            it->second.index = (int)dds.size();
+            P.getrf_dd[gi] = it->second.index;
+            DiagDense<T> dd;
+            memset(&dd, 0, sizeof dd);
+            const pangulu_storage_slot_t* lo = P.getrf_slot[gi];
+            const pangulu_storage_slot_t* up = lo->related_block;
+            if (it->second.u)
+            {
+                dd.u = (T*)nullptr + total;  // offset for now
+                total += tri;
+                for (int r = 0; r < nb; ++r)
+                    for (u32 e = r ? up->columnpointer[r] : 0u; e < up->columnpointer[r + 1]; ++e) dd.umask[r / 16] |= 1u << (up->rowindex[e] / 16);
+            }
+            else dd.u = (T*)nullptr - 1;
+            if (it->second.lt)
+            {
+                dd.lt = (T*)nullptr + total;
+                total += tri;
+                for (int k = 0; k < nb; ++k)
+                    for (u32 e = k ? lo->columnpointer[k] : 0u; e < lo->columnpointer[k + 1]; ++e) dd.ltmask[k / 16] |= 1u << (lo->rowindex[e] / 16);
+            }
+            else dd.lt = (T*)nullptr - 1;
+            dds.push_back(dd);
+        }
+        if (!dds.empty())
+        {
+            CK(cudaMalloc(&pl->diag_dense_buf, total * sizeof(T) + 256));
+            CK(cudaMemset(pl->diag_dense_buf, 0, total * sizeof(T) + 256));
+            for (DiagDense<T>& dd : dds)
+            {
+                dd.u = dd.u == (T*)nullptr - 1 ? nullptr : (T*)pl->diag_dense_buf + (dd.u - (T*)nullptr);
+                dd.lt = dd.lt == (T*)nullptr - 1 ? nullptr : (T*)pl->diag_dense_buf + (dd.lt - (T*)nullptr);
+            }
+        }
+        // per panel run: compact tasks to the back, described by slices of PSM_CP_ROWS compact rows / columns
+        for (size_t si = 0; si + 1 < P.steps.size(); ++si)
+        {
+            Step& st = P.steps[si];
+            Step& cs = P.steps[si + 1];
+            if (st.kind != K_TSTRF || cs.kind != K_CPANEL) continue;
+            std::vector<size_t> order;
+            for (size_t i = st.off; i < st.off + st.count; ++i) if (!compact[i]) order.push_back(i);
+            const size_t nplain = order.size();
+            for (size_t i = st.off; i < st.off + st.count; ++i) if (compact[i]) order.push_back(i);
+            std::vector<PanelTask<T>> tp;
+            std::vector<const pangulu_storage_slot_t*> ts, td;
+            std::vector<char> tc;
+            for (size_t i : order) { tp.push_back(P.panel[i]); ts.push_back(P.panel_slot[i]); td.push_back(diag_of[i]); tc.push_back(compact[i]); }
+            for (size_t k = 0; k < order.size(); ++k)
+            {
+                P.panel[st.off + k] = tp[k]; P.panel_slot[st.off + k] = ts[k]; diag_of[st.off + k] = td[k]; compact[st.off + k] = tc[k];
+            }
+            cs.off = st.off + nplain;
+            cs.count = st.count - nplain;
+            st.count = nplain;
+            cs.aux_off = P.cptasks.size();
+            for (size_t i = cs.off; i < cs.off + cs.count; ++i)
+            {
+                const int dd = need[diag_of[i]].index;
+                const u32 cnt = R_cnt(pl->reg, P.panel[i].dense);
+                for (u32 r0 = 0; r0 < cnt; r0 += PSM_CP_ROWS) P.cptasks.push_back({(int)i, dd, (int)r0});
+            }
+            cs.aux_count = P.cptasks.size() - cs.aux_off;
+        }
+    }
+    const size_t b0 = vbytes(P.getrf), b1 = vbytes(P.panel), b2 = vbytes(P.dests), b3 = vbytes(P.pairs), b4 = vbytes(P.cpairs), b5 = vbytes(ops), b6 = vbytes(P.ctasks);
+    const size_t b7 = vbytes(P.cptasks), b8 = vbytes(dds), b9 = vbytes(P.getrf_dd);
     char* d = nullptr;
-    CK(cudaMalloc((void**)&d, b0 + b1 + b2 + b3 + b4 + b5 + 256));
+    CK(cudaMalloc((void**)&d, b0 + b1 + b2 + b3 + b4 + b5 + b6 + b7 + b8 + b9 + 256));
     pl->dev_buf = d;
     if (!P.cpairs.empty()) CK(cudaMemcpy(d + b0 + b1 + b2 + b3, P.cpairs.data(), P.cpairs.size() * sizeof(CPair), cudaMemcpyHostToDevice));
     if (!ops.empty()) CK(cudaMemcpy(d + b0 + b1 + b2 + b3 + b4, ops.data(), ops.size() * sizeof(DenseOp<T>), cudaMemcpyHostToDevice));
     pl->D.cpairs = (CPair*)(d + b0 + b1 + b2 + b3);
     pl->D.ops = ops.empty() ? nullptr : (DenseOp<T>*)(d + b0 + b1 + b2 + b3 + b4);
+    if (!P.ctasks.empty()) CK(cudaMemcpy(d + b0 + b1 + b2 + b3 + b4 + b5, P.ctasks.data(), P.ctasks.size() * sizeof(CTileTask), cudaMemcpyHostToDevice));
+    pl->D.ctasks = (CTileTask*)(d + b0 + b1 + b2 + b3 + b4 + b5);
+    {
+        char* q = d + b0 + b1 + b2 + b3 + b4 + b5 + b6;
+        if (!P.cptasks.empty()) CK(cudaMemcpy(q, P.cptasks.data(), P.cptasks.size() * sizeof(CPanelTask), cudaMemcpyHostToDevice));
+        pl->D.cptasks = (CPanelTask*)q;
+        q += b7;
+        if (!dds.empty()) CK(cudaMemcpy(q, dds.data(), dds.size() * sizeof(DiagDense<T>), cudaMemcpyHostToDevice));
+        pl->D.dds = dds.empty() ? nullptr : (DiagDense<T>*)q;
+        q += b8;
+        if (!P.getrf_dd.empty()) CK(cudaMemcpy(q, P.getrf_dd.data(), P.getrf_dd.size() * sizeof(int), cudaMemcpyHostToDevice));
+        pl->D.getrf_dd = dds.empty() ? nullptr : (int*)q;
+    }
     if (!P.getrf.empty()) CK(cudaMemcpy(d, P.getrf.data(), P.getrf.size() * sizeof(GetrfTask<T>), cudaMemcpyHostToDevice));
     if (!P.panel.empty()) CK(cudaMemcpy(d + b0, P.panel.data(), P.panel.size() * sizeof(PanelTask<T>), cudaMemcpyHostToDevice));
     if (!P.dests.empty()) CK(cudaMemcpy(d + b0 + b1, P.dests.data(), P.dests.size() * sizeof(SsssmDest<T>), cudaMemcpyHostToDevice));
@@ -1235,6 +1454,10 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     std::vector<SsssmDest<T>>().swap(P.dests);
     std::vector<SsssmPair<T>>().swap(P.pairs);
     std::vector<CPair>().swap(P.cpairs);
+    std::vector<CTileTask>().swap(P.ctasks);
+    std::vector<CPanelTask>().swap(P.cptasks);
+    std::vector<const pangulu_storage_slot_t*>().swap(P.getrf_slot);
+    std::vector<u16>().swap(pl->reg.meta);
     std::vector<const pangulu_storage_slot_t*>().swap(P.panel_slot);
     return pl;
 }
@@ -1282,6 +1505,7 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan* pl)
     if (pl->push_buf) CK(cudaFree(pl->push_buf));
     if (pl->dense_buf) CK(cudaFree(pl->dense_buf));
     if (pl->dense_meta) CK(cudaFree(pl->dense_meta));
+    if (pl->diag_dense_buf) CK(cudaFree(pl->diag_dense_buf));
     delete pl;
 }
 

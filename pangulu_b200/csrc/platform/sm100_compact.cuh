@@ -48,8 +48,7 @@ struct DenseOp
     u32 ld;                // A: leading dimension of a k column;  B: unused
     u32 kmask;             // bit c set: k-chunk c has entries
     u32 pad;
-    u16 tile_start[18];    // B: number of non-empty columns below column 16*t, t = 0..nb/16
-    u16 pad2[2];
+    const u16* pre;        // B: nb+1 entries, pre[c] = number of non-empty columns below column c
 };
 struct CPair { int a, b; };
 
@@ -87,7 +86,8 @@ __device__ __forceinline__ void dmma884c(double& c0, double& c1, double a, doubl
 }
 
 // shared-memory footprint of the compact tile routine
-template <class T, int TN, int STAGES>
+#define PSM_CT_NSLOT 8      // mbarrier pairs = maximum pipeline depth
+template <class T, int TN, int MAXST>
 struct CtLayout
 {
     static constexpr int LDC = 258;                      // accumulator tile: [TN][LDC] (nb <= 256; 258 = 2 mod 16: conflict-free adds)
@@ -95,11 +95,12 @@ struct CtLayout
     static constexpr size_t acc_bytes = (size_t)TN * LDC * sizeof(T);
     static constexpr size_t a_bytes = (size_t)PSM_CT_KC * LDA_MAX * sizeof(T);
     static constexpr size_t b_bytes = (size_t)TN * PSM_CT_BLD * sizeof(T);
-    static constexpr size_t stage_bytes = a_bytes + b_bytes;
-    static constexpr size_t pc_off = acc_bytes + STAGES * stage_bytes;
+    static constexpr size_t ring_bytes = MAXST * (a_bytes + b_bytes);   // MAXST chunks of the largest possible operands
+    static constexpr size_t pc_off = acc_bytes + ring_bytes;
     static constexpr size_t pc_bytes = (size_t)PSM_CT_BATCH * 48;
     static constexpr size_t item_off = pc_off + pc_bytes;
-    static constexpr size_t total = item_off + (size_t)PSM_CT_BATCH * 16 * 2 + 64;
+    static constexpr size_t rank_off = item_off + (size_t)PSM_CT_BATCH * 16 * 2;
+    static constexpr size_t total = rank_off + 256 + 2 * TN + 64;
 };
 
 struct CtPairSm   // one staged operand pair (48 bytes)
@@ -113,60 +114,88 @@ struct CtPairSm   // one staged operand pair (48 bytes)
     u32 first_item;
 };
 
-// tile-size traits: FP64 real uses the DMMA warp grid (8 x 2 warps of 32 x 16), everything else an FMA tile
-template <class T> struct ct_traits { static constexpr int TN = 32, STAGES = 3; };
+// tile-size traits: columns per destination tile and ring size (in chunks of the largest operands)
+template <class T> struct ct_traits { static constexpr int TN = 32, STAGES = 4; };
 template <> struct ct_traits<pangulu_sm100_c64> { static constexpr int TN = 16, STAGES = 2; };
 
 // Barrier state of a CTA that runs many compact-tile tasks (persistent executor): the mbarriers live in static shared
-// memory (other task kinds reuse the dynamic part), are initialised once, and their phases advance with `gcount`.
-struct CtState { u32 gcount = 0; bool armed = false; };
+// memory (other task kinds reuse the dynamic part), are initialised once, and every wait flips the barrier's bit.
+struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
 
-template <class T, int TN, int STAGES>
+// One CTA, one tile of the destination: the block columns [clo, chi).  The host cuts the tiles so that neither the
+// destination nor any B operand queued for it has more than TN NON-EMPTY columns in the range (compact column tiles:
+// a block with 40 non-empty columns has 2 tiles, not nb/TN).
+struct CTileTask { int dest, clo, chi; };
+
+template <class T, int TN, int MAXST>
 __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, const SsssmDest<T>& D, const CPair* __restrict__ cpairs,
-                                                const DenseOp<T>* __restrict__ ops, int c0, CtState& st)
+                                                const DenseOp<T>* __restrict__ ops, int clo, int chi, CtState& st)
 {
-    typedef CtLayout<T, TN, STAGES> Lay;
-    constexpr int KC = PSM_CT_KC, BLD = PSM_CT_BLD, LDC = Lay::LDC;
+    typedef CtLayout<T, TN, MAXST> Lay;
+    constexpr int KC = PSM_CT_KC, BLD = PSM_CT_BLD, LDC = Lay::LDC, NSLOT = PSM_CT_NSLOT;
     constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
-    static_assert(!kDouble || TN == 32, "DMMA warp grid is 8 x 2 warps of 32 x 16");
+    static_assert(!kDouble || TN == 32, "DMMA warp grids assume 32-column tiles");
     constexpr int CPT = TN / 16;  // FMA path: columns per thread
     T* acc = reinterpret_cast<T*>(smem_raw);
-    __shared__ __align__(8) unsigned long long bars[2 * STAGES];  // [0,STAGES) full, [STAGES,2*STAGES) empty
+    unsigned char* ring = smem_raw + Lay::acc_bytes;
+    __shared__ __align__(8) unsigned long long bars[2 * NSLOT];  // [0,NSLOT) full, [NSLOT,2*NSLOT) empty
     CtPairSm* pc = reinterpret_cast<CtPairSm*>(smem_raw + Lay::pc_off);
     u16* items = reinterpret_cast<u16*>(smem_raw + Lay::item_off);  // (pair_in_batch << 4) | chunk
-    __shared__ int s_nitems;
+    unsigned char* crank = smem_raw + Lay::rank_off;                // [nb]: position of a column inside this tile, 0xff otherwise
+    u16* ccols = reinterpret_cast<u16*>(smem_raw + Lay::rank_off + 256);  // [TN]: the tile's columns
+    __shared__ int s_nitems, s_slot_bytes, s_wcnt[8], s_ntc;
 
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
     const bool diag = D.u.val != nullptr;
-    const int ncol = min(TN, nb - c0);
-    if (!diag && col_begin(D.c.ptr, c0) == D.c.ptr[c0 + ncol]) return;
 
-    // ---- task prologue: clear the accumulator tile, arm the barriers on first use
-    for (int i = tid; i < TN * LDC; i += 512) acc[i] = zero<T>();
-    if (!st.armed)
+    // ---- task prologue: the tile's columns, a clear accumulator tile, armed barriers
     {
-        if (tid == 0)
+        bool ne = false;
+        if (tid >= clo && tid < chi)
         {
-            for (int s = 0; s < STAGES; ++s) { mbar_init(bars + s, 1); mbar_init(bars + STAGES + s, 16); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            ne = D.c.ptr[tid + 1] > col_begin(D.c.ptr, tid);
+            if (diag) ne = ne || D.u.ptr[tid + 1] > col_begin(D.u.ptr, tid);
         }
-        st.armed = true;
+        const unsigned bal = __ballot_sync(PSM_FULL, ne);
+        if (tid < 256 && lane == 0) s_wcnt[warp] = __popc(bal);
+        for (int i = tid; i < TN * LDC; i += 512) acc[i] = zero<T>();
+        if (!st.armed)
+        {
+            if (tid == 0)
+            {
+                for (int s = 0; s < NSLOT; ++s) { mbar_init(bars + s, 1); mbar_init(bars + NSLOT + s, 16); }
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            st.armed = true;
+        }
+        // the ring may hold generic-proxy writes of earlier tasks of this CTA; order them before the bulk copies
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid < 256)
+        {
+            int before = 0;
+            for (int w = 0; w < warp; ++w) before += s_wcnt[w];
+            const int rank = before + __popc(bal & ((1u << lane) - 1u));
+            const bool mine = ne && rank < TN;
+            crank[tid] = mine ? (unsigned char)rank : (unsigned char)0xff;
+            if (mine) ccols[rank] = (u16)tid;
+            if (tid == 255) s_ntc = min(TN, before + __popc(bal));
+        }
+        __syncthreads();
     }
-    // the stage buffers may hold generic-proxy writes of earlier tasks of this CTA; order them before the bulk copies
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
+    const int ncol = s_ntc;
+    if (ncol == 0) return;
+    const int cfirst = clo, clast = chi - 1;
 
-    // warp tiling
-    const int wn = warp & 1, wm = warp >> 1;          // DMMA: rows wm*32.., columns wn*16..
-    const int m_base = wm * 32, n_base = wn * 16;
+    // ---- thread roles
     const int lr = lane / 4, lk = lane % 4, lc = (lane % 4) * 2;
     const int tx = lane, ty = warp;                   // FMA: rows tx + 32 i, columns ty*CPT ..
     constexpr int NACC = kDouble ? 16 : 8 * CPT;
     T racc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) racc[i] = zero<T>();
+    u32 full_bits = st.full_bits, empty_bits = st.empty_bits;
 
-    u32 gcount = st.gcount;  // items consumed so far by this CTA (stage = gcount % STAGES, phase = (gcount / STAGES) & 1)
     for (u32 pb = D.pair_begin; pb < D.pair_end; pb += PSM_CT_BATCH)
     {
         const int npb = (int)min((u32)PSM_CT_BATCH, D.pair_end - pb);
@@ -175,23 +204,25 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
         if (warp == 0)
         {
             u32 km = 0;
+            int bytes = 0;
             CtPairSm e;
             if (lane < npb)
             {
                 const CPair cp = cpairs[pb + lane];
                 const DenseOp<T>& A = ops[cp.a];
                 const DenseOp<T>& B = ops[cp.b];
-                const u32 n0 = B.tile_start[c0 / 16], n1 = B.tile_start[(c0 + ncol + 15) / 16];
+                const u32 n0 = B.pre[cfirst], n1 = B.pre[clast + 1];
                 e.a_dense = A.dense;
                 e.b_dense = B.dense + (size_t)n0 * BLD;
                 e.rows = A.list;
                 e.cols = B.list + n0;
                 e.m = (u16)A.cnt;
                 e.ld = (u16)A.ld;
-                e.nt = (u16)(n1 - n0);
+                e.nt = (u16)min(n1 - n0, (u32)TN);
                 e.nprime = (u16)B.cnt;
                 km = (n1 > n0) ? (A.kmask & B.kmask) : 0u;
                 e.kmask = km;
+                if (km) bytes = (int)((KC * A.ld + e.nt * BLD) * sizeof(T));
             }
             const int cnt = __popc(km);
             int off = cnt;
@@ -200,8 +231,9 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
             {
                 const int v = __shfl_up_sync(PSM_FULL, off, o);
                 if (lane >= o) off += v;
+                bytes = max(bytes, __shfl_xor_sync(PSM_FULL, bytes, o));
             }
-            if (lane == 31) s_nitems = off;
+            if (lane == 31) { s_nitems = off; s_slot_bytes = (bytes + 127) & ~127; }
             off -= cnt;
             if (lane < npb)
             {
@@ -219,18 +251,21 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
         __syncthreads();
         const int nitems = s_nitems;
         if (nitems == 0) continue;
+        const int slot_bytes = s_slot_bytes;
+        const int nst = min(NSLOT, (int)(Lay::ring_bytes / (size_t)slot_bytes));  // >= MAXST by construction
+        const int LA = nst - 1;
 
-        // ---- software pipeline: iteration i issues the bulk copies of item i and consumes item i - (STAGES-1)
         int cur_pair = -1;
         u16 rfull[4] = {0xffff, 0xffff, 0xffff, 0xffff}, cfull[4] = {0xffff, 0xffff, 0xffff, 0xffff};
         u16 rf8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rf8[i] = 0xffff;
         int cur_m = 0, cur_nt = 0, cur_ld = 0;
+        int m_base = 0, n_base = 0, mtc = 0, ntc = 0;   // DMMA: this warp's piece of the current pair
 
         auto flush = [&]() {
-            // registers -> accumulator tile in full coordinates.  Which warp owns an element of the tile depends on the
-            // pair's compaction, and warps drift apart by up to STAGES-1 items: the barrier keeps the adds of
+            // registers -> accumulator tile in full row coordinates.  Which warp owns an element of the tile depends on the
+            // pair's compaction, and warps drift apart by up to nst-1 items: the barrier keeps the adds of
             // consecutive pairs apart (every warp passes here once per pair, with or without work).
             __syncthreads();
             if constexpr (kDouble)
@@ -260,29 +295,29 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                     {
                         const u16 r = rf8[i], c = cfull[j];
                         T& v = racc[i * CPT + j];
-                        if (r != 0xffff && c != 0xffff) { T t = acc[(int)c * LDC + r]; vadd(t, v); acc[(int)c * LDC + r] = t; }
+                        if (r != 0xffff && c != 0xffff) { T tv = acc[(int)c * LDC + r]; vadd(tv, v); acc[(int)c * LDC + r] = tv; }
                         v = zero<T>();
                     }
             }
         };
 
-        for (int i = 0; i < nitems + STAGES - 1; ++i)
+        // ---- software pipeline: iteration i issues the bulk copies of item i and consumes item i - LA
+        for (int i = 0; i < nitems + LA; ++i)
         {
             if (tid == 0 && i < nitems)
             {
-                const u32 g = gcount + (u32)i;
-                const int s = (int)(g % STAGES);
-                if (g >= (u32)STAGES) mbar_wait(bars + STAGES + s, ((g / STAGES) - 1) & 1);  // consumers released the stage
+                const int s = i % nst;
+                if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
                 const u16 it = items[i];
                 const CtPairSm& e = pc[it >> 4];
                 const int ch = it & 15;
-                unsigned char* sb = smem_raw + Lay::acc_bytes + (size_t)s * Lay::stage_bytes;
+                unsigned char* sb = ring + (size_t)s * slot_bytes;
                 const u32 abytes = (u32)(KC * e.ld * sizeof(T)), bbytes = (u32)(e.nt * BLD * sizeof(T));
                 mbar_expect_tx(bars + s, abytes + bbytes);
                 bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
-                bulk_g2s(sb + Lay::a_bytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
+                bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
             }
-            const int ci = i - (STAGES - 1);
+            const int ci = i - LA;
             if (ci < 0) continue;
             const u16 it = items[ci];
             const int pl = it >> 4;
@@ -294,17 +329,35 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                 cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
                 if constexpr (kDouble)
                 {
+                    // warp grid by operand height: 8 x 2 warps of 32 x 16 (tall), else 4 x 4 warps of (8|16|32) x 8 -- the four
+                    // row groups of the small grids sit on the four SM sub-partitions even when only one column group has work
+                    const int mpad = (cur_m + 7) & ~7, MT = mpad / 8;
+                    if (MT > 16)
+                    {
+                        m_base = (warp >> 1) * 32; n_base = (warp & 1) * 16;
+                        mtc = min(4, max(0, (mpad - m_base) / 8));
+                        ntc = min(2, max(0, (cur_nt + 7 - n_base) / 8));
+                    }
+                    else
+                    {
+                        const int tm = MT > 8 ? 4 : MT > 4 ? 2 : 1;
+                        m_base = (warp & 3) * tm * 8; n_base = (warp >> 2) * 8;
+                        mtc = min(tm, max(0, (mpad - m_base) / 8));
+                        ntc = cur_nt > n_base ? 1 : 0;
+                    }
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                     {
                         const int r = m_base + mt * 8 + lr;
-                        rfull[mt] = r < cur_m ? e.rows[r] : (u16)0xffff;
+                        rfull[mt] = (mt < mtc && r < cur_m) ? e.rows[r] : (u16)0xffff;
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                     {
                         const int c = n_base + (q >> 1) * 8 + lc + (q & 1);
-                        cfull[q] = c < cur_nt ? (u16)(e.cols[c] - c0) : (u16)0xffff;
+                        u16 v = 0xffff;
+                        if ((q >> 1) < ntc && c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
+                        cfull[q] = v;
                     }
                 }
                 else
@@ -319,20 +372,19 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                     for (int j = 0; j < CPT; ++j)
                     {
                         const int c = ty * CPT + j;
-                        cfull[j] = c < cur_nt ? (u16)(e.cols[c] - c0) : (u16)0xffff;
+                        u16 v = 0xffff;
+                        if (c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
+                        cfull[j] = v;
                     }
                 }
             }
-            const u32 g = gcount + (u32)ci;
-            const int s = (int)(g % STAGES);
-            mbar_wait(bars + s, (g / STAGES) & 1);
-            const T* As = reinterpret_cast<const T*>(smem_raw + Lay::acc_bytes + (size_t)s * Lay::stage_bytes);
-            const T* Bs = reinterpret_cast<const T*>(smem_raw + Lay::acc_bytes + (size_t)s * Lay::stage_bytes + Lay::a_bytes);
+            const int s = ci % nst;
+            mbar_wait(bars + s, (full_bits >> s) & 1u);
+            full_bits ^= 1u << s;
+            const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes);
+            const T* Bs = As + KC * cur_ld;
             if constexpr (kDouble)
             {
-                const int mpad = (cur_m + 7) & ~7;
-                const int mtc = min(4, max(0, (mpad - m_base) / 8));
-                const int ntc = min(2, max(0, (cur_nt + 7 - n_base) / 8));
                 if (mtc > 0 && ntc > 0)
                 {
                     const double* Ap = As + lk * cur_ld + m_base + lr;
@@ -378,19 +430,26 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bars + STAGES + s);
+            if (lane == 0) mbar_arrive(bars + NSLOT + s);
         }
         if (cur_pair >= 0) flush();
-        gcount += (u32)nitems;
+        // every release must be matched by a wait of the producer, so the barrier bits stay in step
+        if (tid == 0)
+            for (int j = max(0, nitems - nst); j < nitems; ++j)
+            {
+                const int s = j % nst;
+                mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u);
+                empty_bits ^= 1u << s;
+            }
     }
-
-    st.gcount = gcount;
+    st.full_bits = full_bits;
+    st.empty_bits = empty_bits;
 
     // ---- epilogue: accumulator tile -> destination pattern (other CTAs may update the same block: reductions)
     __syncthreads();
     for (int jj = warp; jj < ncol; jj += 16)
     {
-        const int j = c0 + jj;
+        const int j = ccols[jj];
         const u32 e0 = col_begin(D.c.ptr, j), e1 = D.c.ptr[j + 1];
         const T* Cj = acc + jj * LDC;
         for (u32 e = e0 + lane; e < e1; e += PSM_WARP)
@@ -401,21 +460,24 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
     }
     if (diag)
     {
-        for (int r = tid; r < min(nb, c0 + ncol); r += 512)
+        // upper CSR half: row r holds columns >= r ascending; the tile's columns lie in [cfirst, clast]
+        for (int r = tid; r <= min(nb - 1, clast); r += 512)
         {
             const u32 r0 = col_begin(D.u.ptr, r), r1 = D.u.ptr[r + 1];
             u32 lo = r0, hi = r1;
             while (lo < hi)
             {
                 const u32 mid = (lo + hi) >> 1;
-                if ((int)D.u.idx[mid] < c0) lo = mid + 1;
+                if ((int)D.u.idx[mid] < cfirst) lo = mid + 1;
                 else hi = mid;
             }
             for (u32 e = lo; e < r1; ++e)
             {
                 const int c = D.u.idx[e];
-                if (c >= c0 + ncol) break;
-                const T v = acc[(c - c0) * LDC + r];
+                if (c > clast) break;
+                const unsigned char rk = crank[c];
+                if (rk == 0xff) continue;
+                const T v = acc[(int)rk * LDC + r];
                 if (!is_zero(v)) red_sub(&D.u.val[e], v);
             }
         }
@@ -423,17 +485,18 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
     __syncthreads();  // the accumulator tile is free again
 }
 
+// stand-alone launch (per-wave executor): one CTA per tile task
 template <class T>
 __global__ void __launch_bounds__(512, 1)
-ssssm_ctile_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const CPair* __restrict__ cpairs, const DenseOp<T>* __restrict__ ops, int tiles_per_dest)
+ssssm_ctile_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const CPair* __restrict__ cpairs, const DenseOp<T>* __restrict__ ops,
+                   const CTileTask* __restrict__ ctasks)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TN = ct_traits<T>::TN;
-    const int d = blockIdx.x / tiles_per_dest;
-    const int c0 = (blockIdx.x % tiles_per_dest) * TN;
-    const SsssmDest<T> D = dests[d];
+    const CTileTask ct = ctasks[blockIdx.x];
+    const SsssmDest<T> D = dests[ct.dest];
     CtState st;
-    ssssm_ctile_cta<T, TN, ct_traits<T>::STAGES>(smem_raw, nb, D, cpairs, ops, c0, st);
+    ssssm_ctile_cta<T, TN, ct_traits<T>::STAGES>(smem_raw, nb, D, cpairs, ops, ct.clo, ct.chi, st);
 }
 
 // Write one finished value of a block into its compact dense copy (called by the panel-solve warps).
@@ -445,6 +508,267 @@ template <class T>
 __device__ __forceinline__ void dense_store_b(const DenseOp<T>& B, int k, int cprime, T v)
 {
     B.dense[((size_t)(k / PSM_CT_KC) * B.cnt + cprime) * PSM_CT_BLD + (k % PSM_CT_KC)] = v;
+}
+
+
+// ================================================================================================
+// TSTRF / GESSM on compact dense data ("compact panel" path).
+//
+// A panel block that has a compact dense copy is solved as a dense triangular system over its non-empty
+// rows (TSTRF: X U = B) or columns (GESSM: L X = B, i.e. X^T L^T = B^T).  With
+//     X[k][s] = B(rows[r0+s], k)  (TSTRF)   /   B(k, cols[r0+s])  (GESSM),   s < 64,  k < nb
+//     Tm      = U                 (TSTRF)   /   L^T                 (GESSM)
+// both are   X[c][s] = (X[c][s] - sum_{k<c} X[k][s] Tm(k,c)) / Tm(c,c)   (no division for GESSM: unit diagonal).
+// One CTA takes 64 compact rows/columns.  The k range is processed in chunks of 16 (only chunks in which the block
+// has entries): the contribution of all earlier chunks is a dense 64 x 16 x (16 K) product on the DMMA pipe (X is kept
+// in shared memory in the A-operand layout [k][68], Tm arrives by TMA in the B-operand layout [chunk][column][20]
+// that the GETRF task wrote), followed by a 16-column substitution with one thread per row -- the same operations
+// on every entry as the reference's row/column sweeps (pangulu_platform_0100000.c:137-209), in blocked order.
+// Results go to the block's CSC value array and to its compact dense copy.
+// ================================================================================================
+template <class T>
+struct DiagDense
+{
+    T* u;            // U   (upper half incl. diagonal) in the B-operand layout [chunk][nb][20], or null
+    T* lt;           // L^T (strict lower half, transposed), same layout, or null
+    u32 umask[16];   // umask[K] bit J: sub-block (rows 16K.., columns 16J..) of U has entries
+    u32 ltmask[16];
+};
+
+#define PSM_CP_ROWS 64
+#define PSM_CP_LDX 68
+
+template <class T>
+struct CpLayout
+{
+    static constexpr size_t x_bytes = (size_t)256 * PSM_CP_LDX * sizeof(T);
+    static constexpr size_t sub_bytes = (size_t)16 * PSM_CT_BLD * sizeof(T);     // one 16 x 16 sub-block of Tm
+    static constexpr size_t tbuf_bytes = 16 * sub_bytes;                            // one column block (all K)
+    static constexpr size_t total = x_bytes + 2 * tbuf_bytes + 64;
+};
+
+struct CpState { u32 bits = 0; bool armed = false; };
+
+// GETRF epilogue: scatter the finished halves of a diagonal block into its dense triangular copies
+template <class T>
+__device__ __forceinline__ void diag_densify(int nb, const GetrfTask<T>& G, const DiagDense<T>& DD)
+{
+    const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP, nw = blockDim.x / PSM_WARP;
+    if (DD.u)
+        for (int r = warp; r < nb; r += nw)   // row r of U (CSR, diagonal first)
+            for (u32 e = col_begin(G.upper.ptr, r) + lane; e < G.upper.ptr[r + 1]; e += PSM_WARP)
+                DD.u[((size_t)(r / 16) * nb + G.upper.idx[e]) * PSM_CT_BLD + (r % 16)] = G.upper.val[e];
+    if (DD.lt)
+        for (int k = warp; k < nb; k += nw)   // column k of L (CSC): L(c,k) = L^T(k,c)
+            for (u32 e = col_begin(G.lower.ptr, k) + lane; e < G.lower.ptr[k + 1]; e += PSM_WARP)
+                DD.lt[((size_t)(k / 16) * nb + G.lower.idx[e]) * PSM_CT_BLD + (k % 16)] = G.lower.val[e];
+}
+
+template <class T>
+__device__ __forceinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, const PanelTask<T>& Q, const DenseOp<T>& Dn, const DiagDense<T>& DD,
+                                                  int r0, CpState& st)
+{
+    typedef CpLayout<T> Lay;
+    constexpr int LDX = PSM_CP_LDX, BLD = PSM_CT_BLD, R = PSM_CP_ROWS;
+    constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
+    T* X = reinterpret_cast<T*>(smem_raw);                               // [nb][LDX]
+    unsigned char* tb0 = smem_raw + Lay::x_bytes;                         // 2 x [16 K][16 cols][20]
+    __shared__ __align__(8) unsigned long long cbars[2];
+    const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
+    const bool gessm = Q.kind == PANGULU_TASK_GESSM;
+    const T* Tm = gessm ? DD.lt : DD.u;
+    const u32* tmask = gessm ? DD.ltmask : DD.umask;
+    const u32 kmask = Dn.kmask;
+    const int nrows = min(R, (int)Dn.cnt - r0);   // compact rows / columns of this slice
+    const Blk<T> B = Q.b;
+
+    if (!st.armed)
+    {
+        if (tid == 0)
+        {
+            mbar_init(cbars + 0, 1);
+            mbar_init(cbars + 1, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        st.armed = true;
+    }
+    // ---- X <- 0 on the block's k-chunks, then gather the slice from the CSC arrays
+    for (int ch = 0; ch < nb / 16; ++ch)
+        if ((kmask >> ch) & 1u)
+            for (int i = tid; i < 16 * LDX; i += 512) X[ch * 16 * LDX + i] = zero<T>();
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // producer: the column block of Tm for chunk J -> buffer `par`; one bulk copy per needed 16 x 16 sub-block
+    auto issue = [&](int J, int par) {
+        unsigned char* tb = tb0 + (size_t)par * Lay::tbuf_bytes;
+        u32 need = 0;
+        for (int K = 0; K <= J; ++K)
+            if (((kmask >> K) & 1u) && (K == J || ((tmask[K] >> J) & 1u))) need |= 1u << K;
+        mbar_expect_tx(cbars + par, (u32)(__popc(need) * Lay::sub_bytes));
+        for (int K = 0; K <= J; ++K)
+            if ((need >> K) & 1u)
+                bulk_g2s(tb + (size_t)K * Lay::sub_bytes, Tm + ((size_t)K * nb + 16 * J) * BLD, (u32)Lay::sub_bytes, cbars + par);
+    };
+    int Jcur = kmask ? (__ffs(kmask) - 1) : -1;
+    int par = 0;
+    if (tid == 0 && Jcur >= 0) issue(Jcur, 0);
+    if (gessm)
+    {
+        for (int s = warp; s < nrows; s += 16)
+        {
+            const int c = Dn.list[r0 + s];
+            for (u32 e = col_begin(B.ptr, c) + lane; e < B.ptr[c + 1]; e += PSM_WARP) X[(int)B.idx[e] * LDX + s] = B.val[e];
+        }
+    }
+    else
+    {
+        for (int k = warp; k < nb; k += 16)
+            for (u32 e = col_begin(B.ptr, k) + lane; e < B.ptr[k + 1]; e += PSM_WARP)
+            {
+                const int s = (int)Dn.inv[B.idx[e]] - r0;
+                if (s >= 0 && s < R) X[k * LDX + s] = B.val[e];
+            }
+    }
+    __syncthreads();
+
+    const int lr = lane / 4, lk = lane % 4, lc = (lane % 4) * 2;
+    const int mtile = warp & 7, ntile = warp >> 3;
+    u32 bits = st.bits;
+    while (Jcur >= 0)
+    {
+        const u32 rest = kmask & ~((2u << Jcur) - 1u);
+        const int Jnext = rest ? (__ffs(rest) - 1) : -1;
+        if (tid == 0 && Jnext >= 0) issue(Jnext, par ^ 1);   // prefetch the next column block
+        mbar_wait(cbars + par, (bits >> par) & 1u);
+        bits ^= 1u << par;
+        const T* Tb = reinterpret_cast<const T*>(tb0 + (size_t)par * Lay::tbuf_bytes);
+        // ---- X[:, J] -= X[:, <J] Tm(<J, J)
+        u32 need = 0;
+        for (int K = 0; K < Jcur; ++K)
+            if (((kmask >> K) & 1u) && ((tmask[K] >> Jcur) & 1u)) need |= 1u << K;
+        if (need)
+        {
+            if constexpr (kDouble)
+            {
+                double a0 = 0, a1 = 0, b0 = 0, b1 = 0;   // two accumulator pairs (k4 parity) for DMMA latency
+                u32 nk = need;
+                while (nk)
+                {
+                    const int K = __ffs(nk) - 1;
+                    nk &= nk - 1;
+                    const double* Ap = X + (K * 16 + lk) * LDX + mtile * 8 + lr;
+                    const double* Bp = Tb + (size_t)K * 16 * BLD + (ntile * 8 + lr) * BLD + lk;
+                    dmma884c(a0, a1, Ap[0], Bp[0]);
+                    dmma884c(b0, b1, Ap[4 * LDX], Bp[4]);
+                    dmma884c(a0, a1, Ap[8 * LDX], Bp[8]);
+                    dmma884c(b0, b1, Ap[12 * LDX], Bp[12]);
+                }
+                double* Xo = X + (Jcur * 16 + ntile * 8 + lc) * LDX + mtile * 8 + lr;
+                Xo[0] -= a0 + b0;
+                Xo[LDX] -= a1 + b1;
+            }
+            else
+            {
+                // FMA: thread = (row s = tid % 64, column pair cg = tid / 64)
+                const int s = tid % 64, cg = tid / 64;
+                T acc0 = zero<T>(), acc1 = zero<T>();
+                u32 nk = need;
+                while (nk)
+                {
+                    const int K = __ffs(nk) - 1;
+                    nk &= nk - 1;
+                    const T* Tk = Tb + (size_t)K * 16 * BLD;
+#pragma unroll 4
+                    for (int kk = 0; kk < 16; ++kk)
+                    {
+                        const T xv = X[(K * 16 + kk) * LDX + s];
+                        fma_acc(acc0, xv, Tk[(cg * 2) * BLD + kk]);
+                        fma_acc(acc1, xv, Tk[(cg * 2 + 1) * BLD + kk]);
+                    }
+                }
+                vsub(X[(Jcur * 16 + cg * 2) * LDX + s], acc0);
+                vsub(X[(Jcur * 16 + cg * 2 + 1) * LDX + s], acc1);
+            }
+            __syncthreads();
+        }
+        // ---- 16-column substitution against the diagonal sub-block, one thread per row
+        if (tid < R)
+        {
+            const T* Tjj = Tb + (size_t)Jcur * 16 * BLD;   // Tm(16J + k, 16J + c) at [c*20 + k]
+            T x[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) x[c] = X[(Jcur * 16 + c) * LDX + tid];
+#pragma unroll
+            for (int c = 0; c < 16; ++c)
+            {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < c) fnma(x[c], x[k], Tjj[c * BLD + k]);
+                if (!gessm) x[c] = vdiv(x[c], clamp_pivot(Tjj[c * BLD + c]));
+            }
+#pragma unroll
+            for (int c = 0; c < 16; ++c) X[(Jcur * 16 + c) * LDX + tid] = x[c];
+        }
+        __syncthreads();
+        Jcur = Jnext;
+        par ^= 1;
+    }
+    st.bits = bits;
+
+    // ---- write back: CSC values and the compact dense copy
+    if (gessm)
+    {
+        for (int s = warp; s < nrows; s += 16)
+        {
+            const int c = Dn.list[r0 + s];
+            for (u32 e = col_begin(B.ptr, c) + lane; e < B.ptr[c + 1]; e += PSM_WARP) B.val[e] = X[(int)B.idx[e] * LDX + s];
+        }
+        // dense copy (B-operand layout): (k, c') at ((k/16) n' + c') 20 + k%16 -- 16 consecutive k are contiguous
+        const int nchunk = nb / 16;
+        for (int i = tid; i < nchunk * nrows * 16; i += 512)
+        {
+            const int kk = i % 16, s = (i / 16) % nrows, ch = i / (16 * nrows);
+            if ((kmask >> ch) & 1u) Dn.dense[((size_t)ch * Dn.cnt + r0 + s) * BLD + kk] = X[(ch * 16 + kk) * LDX + s];
+        }
+    }
+    else
+    {
+        for (int k = warp; k < nb; k += 16)
+            for (u32 e = col_begin(B.ptr, k) + lane; e < B.ptr[k + 1]; e += PSM_WARP)
+            {
+                const int s = (int)Dn.inv[B.idx[e]] - r0;
+                if (s >= 0 && s < R) B.val[e] = X[k * LDX + s];
+            }
+        // dense copy (A-operand layout): (r', k) at k ld + r'
+        for (int i = tid; i < nb * nrows; i += 512)
+        {
+            const int s = i % nrows, k = i / nrows;
+            if ((kmask >> (k / 16)) & 1u) Dn.dense[(size_t)k * Dn.ld + r0 + s] = X[k * LDX + s];
+        }
+    }
+    __syncthreads();
+}
+
+template <class T>
+__global__ void diag_densify_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, const int* __restrict__ getrf_dd, const DiagDense<T>* __restrict__ dds)
+{
+    const int dd = getrf_dd ? getrf_dd[blockIdx.x] : -1;
+    if (dd < 0) return;
+    diag_densify<T>(nb, tasks[blockIdx.x], dds[dd]);
+}
+
+// stand-alone launch (per-wave executor)
+struct CPanelTask { int panel, dd, r0; };
+template <class T>
+__global__ void __launch_bounds__(512, 1)
+panel_compact_kernel(int nb, const PanelTask<T>* __restrict__ tasks, const CPanelTask* __restrict__ cpt, const DenseOp<T>* __restrict__ ops,
+                     const DiagDense<T>* __restrict__ dds)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const CPanelTask ct = cpt[blockIdx.x];
+    const PanelTask<T> Q = tasks[ct.panel];
+    CpState st;
+    panel_compact_cta<T>(smem_raw, nb, Q, ops[Q.dense], dds[ct.dd], ct.r0, st);
 }
 
 }  // namespace psm

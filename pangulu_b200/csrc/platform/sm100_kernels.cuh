@@ -1100,7 +1100,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 // ================================================================================================
 struct MegaTask { int kind, a, b, c; };
 template <class T> struct MegaPush { T* peer_val; int* peer_flag; };
-enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6 };
+enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6, MEGA_CPANEL = 7 };
 
 template <class T>
 struct MegaParams
@@ -1113,6 +1113,9 @@ struct MegaParams
     const CPair* cpairs;    // operand pairs of the compact-tile destinations (indices into ops)
     const int2* cpair_dep;  // per compact pair: sync ids of A and B
     const DenseOp<T>* ops;  // compact dense copies of operand blocks
+    const CPanelTask* cptasks;  // slices of the compact panel solves
+    const DiagDense<T>* dds;    // dense triangular copies of diagonal blocks
+    const int* getrf_dd;        // per GETRF task: index into dds or -1
     const int* dest_id;     // per destination descriptor: sync id of the destination
     const GetrfTask<T>* getrf;
     const int2* getrf_id;   // sync ids of the lower and the upper half
@@ -1212,6 +1215,7 @@ mega_kernel(const MegaParams<T> P)
     const int tid = threadIdx.x, warp = tid / PSM_WARP;
     const int nb = P.nb;
     CtState ct_state;
+    CpState cp_state;
     for (;;)
     {
         if (tid == 0) s_ticket = atomicAdd(P.counter, 1);
@@ -1240,7 +1244,7 @@ mega_kernel(const MegaParams<T> P)
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             if (mt.kind == MEGA_CTILE)
-                ssssm_ctile_cta<T, ct_traits<T>::TN, ct_traits<T>::STAGES>(smem_raw, nb, D, P.cpairs, P.ops, mt.b * ct_traits<T>::TN, ct_state);
+                ssssm_ctile_cta<T, ct_traits<T>::TN, ct_traits<T>::STAGES>(smem_raw, nb, D, P.cpairs, P.ops, mt.b & 0xffff, mt.b >> 16, ct_state);
             else if (mt.kind == MEGA_TILE)
                 ssssm_tile2_cta<T, TM>(smem_raw, nb, D, P.pairs, mt.b * PSM_TILE_N, true);
             else
@@ -1276,6 +1280,11 @@ mega_kernel(const MegaParams<T> P)
                 __syncthreads();
                 getrf_body<T, 512>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf);
             }
+            if (P.getrf_dd && P.getrf_dd[mt.a] >= 0)
+            {
+                __syncthreads();  // (the factors were written by other threads of this CTA)
+                diag_densify<T>(nb, G, P.dds[P.getrf_dd[mt.a]]);
+            }
             __threadfence();
             __syncthreads();
             if (tid == 0) { st_release(P.done + id.x, 1); st_release(P.done + id.y, 1); }
@@ -1283,6 +1292,26 @@ mega_kernel(const MegaParams<T> P)
             // push, after which the flag may be raised)
             if (id.x != id.y) push_block<T>(P.push_ptr, P.pushes, id.x, G.lower.val, G.lower.ptr[nb]);
             push_block<T>(P.push_ptr, P.pushes, id.y, G.upper.val, G.upper.ptr[nb]);
+            break;
+        }
+        case MEGA_CPANEL:
+        {
+            const CPanelTask cpt = P.cptasks[mt.a];
+            const PanelTask<T> Q = P.panel[cpt.panel];
+            const int2 id = P.panel_id[cpt.panel];
+            if (tid == 0) { spin_until_set(P.done + id.y, P.multi); spin_until_zero(P.remaining + id.x); }
+            __syncthreads();
+            if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            panel_compact_cta<T>(smem_raw, nb, Q, P.ops[Q.dense], P.dds[cpt.dd], cpt.r0, cp_state);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0)
+            {
+                s_last = atomicSub(P.pending + id.x, 1) == 1;
+                if (s_last) { __threadfence(); st_release(P.done + id.x, 1); }
+            }
+            __syncthreads();
+            if (s_last) push_block<T>(P.push_ptr, P.pushes, id.x, Q.b.val, Q.b.ptr[nb]);
             break;
         }
         case MEGA_PANEL:
