@@ -128,7 +128,7 @@ struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
 struct CTileTask { int dest, clo, chi; };
 
 template <class T, int TN, int MAXST>
-__device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, const SsssmDest<T>& D, const CPair* __restrict__ cpairs,
+__device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, const SsssmDest<T>& D, const CPair* __restrict__ cpairs,
                                                 const DenseOp<T>* __restrict__ ops, int clo, int chi, CtState& st)
 {
     typedef CtLayout<T, TN, MAXST> Lay;
@@ -252,16 +252,18 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
         const int nitems = s_nitems;
         if (nitems == 0) continue;
         const int slot_bytes = s_slot_bytes;
-        const int nst = min(NSLOT, (int)(Lay::ring_bytes / (size_t)slot_bytes));  // >= MAXST by construction
-        const int LA = nst - 1;
+        // pipeline depth: 8 slots when the batch's largest item fits an eighth of the ring, else 4 (>= MAXST by construction)
+        const int nst = ((size_t)slot_bytes * NSLOT <= Lay::ring_bytes) ? NSLOT : (MAXST >= 4 ? 4 : 2);
+        const int smask = nst - 1, LA = nst - 1;
 
-        int cur_pair = -1;
         u16 rfull[4] = {0xffff, 0xffff, 0xffff, 0xffff}, cfull[4] = {0xffff, 0xffff, 0xffff, 0xffff};
         u16 rf8[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) rf8[i] = 0xffff;
         int cur_m = 0, cur_nt = 0, cur_ld = 0;
         int m_base = 0, n_base = 0, mtc = 0, ntc = 0;   // DMMA: this warp's piece of the current pair
+        bool small = false;                             // DMMA: 4 x 4 warp grid (one column group per warp, k-parity accumulators)
+        bool have_prev = false;
 
         auto flush = [&]() {
             // registers -> accumulator tile in full row coordinates.  Which warp owns an element of the tile depends on the
@@ -270,21 +272,39 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
             __syncthreads();
             if constexpr (kDouble)
             {
+                if (mtc > 0 && ntc > 0)
+                {
 #pragma unroll
-                for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                    for (int nt2 = 0; nt2 < 2; ++nt2)
+                    for (int mt = 0; mt < 4; ++mt)
                     {
                         const u16 r = rfull[mt];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h)
+                        if (small)
                         {
-                            const u16 c = cfull[nt2 * 2 + h];
-                            T& v = racc[(mt * 2 + nt2) * 2 + h];
-                            if (r != 0xffff && c != 0xffff) acc[(int)c * LDC + r] += v;
-                            v = zero<T>();
+                            // the second column slot of the register tile held the odd k4 steps
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                            {
+                                const u16 c = cfull[h];
+                                if (r != 0xffff && c != 0xffff) acc[(int)c * LDC + r] += racc[(mt * 2) * 2 + h] + racc[(mt * 2 + 1) * 2 + h];
+                                racc[(mt * 2) * 2 + h] = 0.0;
+                                racc[(mt * 2 + 1) * 2 + h] = 0.0;
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int nt2 = 0; nt2 < 2; ++nt2)
+#pragma unroll
+                                for (int h = 0; h < 2; ++h)
+                                {
+                                    const u16 c = cfull[nt2 * 2 + h];
+                                    T& v = racc[(mt * 2 + nt2) * 2 + h];
+                                    if (r != 0xffff && c != 0xffff) acc[(int)c * LDC + r] += v;
+                                    v = zero<T>();
+                                }
                         }
                     }
+                }
             }
             else
             {
@@ -300,51 +320,55 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                     }
             }
         };
+        // producer step (thread 0): bulk copies of item i into its slot
+        auto produce = [&](int i) {
+            const int s = i & smask;
+            if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
+            const u16 it = items[i];
+            const CtPairSm& e = pc[it >> 4];
+            const int ch = it & 15;
+            unsigned char* sb = ring + (size_t)s * slot_bytes;
+            const u32 abytes = (u32)(KC * e.ld * sizeof(T)), bbytes = (u32)(e.nt * BLD * sizeof(T));
+            mbar_expect_tx(bars + s, abytes + bbytes);
+            bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
+            bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
+        };
+        if (tid == 0)
+            for (int i = 0; i < min(LA, nitems); ++i) produce(i);
 
-        // ---- software pipeline: iteration i issues the bulk copies of item i and consumes item i - LA
-        for (int i = 0; i < nitems + LA; ++i)
+        // ---- pairs of the batch; items of a pair are consecutive in the item list
+        int ci = 0;
+        for (int pl = 0; pl < npb; ++pl)
         {
-            if (tid == 0 && i < nitems)
+            const CtPairSm& e = pc[pl];
+            const int cnt = __popc(e.kmask);
+            if (cnt == 0) continue;
+            if (have_prev) flush();
+            have_prev = true;
+            cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
+            bool active;
+            if constexpr (kDouble)
             {
-                const int s = i % nst;
-                if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
-                const u16 it = items[i];
-                const CtPairSm& e = pc[it >> 4];
-                const int ch = it & 15;
-                unsigned char* sb = ring + (size_t)s * slot_bytes;
-                const u32 abytes = (u32)(KC * e.ld * sizeof(T)), bbytes = (u32)(e.nt * BLD * sizeof(T));
-                mbar_expect_tx(bars + s, abytes + bbytes);
-                bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
-                bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
-            }
-            const int ci = i - LA;
-            if (ci < 0) continue;
-            const u16 it = items[ci];
-            const int pl = it >> 4;
-            if (pl != cur_pair)
-            {
-                if (cur_pair >= 0) flush();
-                cur_pair = pl;
-                const CtPairSm& e = pc[pl];
-                cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
-                if constexpr (kDouble)
+                // warp grid by operand height: 8 x 2 warps of 32 x 16 (tall), else 4 x 4 warps of (8|16|32) x 8 -- the four
+                // row groups of the small grids sit on the four SM sub-partitions even when only one column group has work
+                const int mpad = (cur_m + 7) & ~7, MT = mpad / 8;
+                small = MT <= 16;
+                if (!small)
                 {
-                    // warp grid by operand height: 8 x 2 warps of 32 x 16 (tall), else 4 x 4 warps of (8|16|32) x 8 -- the four
-                    // row groups of the small grids sit on the four SM sub-partitions even when only one column group has work
-                    const int mpad = (cur_m + 7) & ~7, MT = mpad / 8;
-                    if (MT > 16)
-                    {
-                        m_base = (warp >> 1) * 32; n_base = (warp & 1) * 16;
-                        mtc = min(4, max(0, (mpad - m_base) / 8));
-                        ntc = min(2, max(0, (cur_nt + 7 - n_base) / 8));
-                    }
-                    else
-                    {
-                        const int tm = MT > 8 ? 4 : MT > 4 ? 2 : 1;
-                        m_base = (warp & 3) * tm * 8; n_base = (warp >> 2) * 8;
-                        mtc = min(tm, max(0, (mpad - m_base) / 8));
-                        ntc = cur_nt > n_base ? 1 : 0;
-                    }
+                    m_base = (warp >> 1) * 32; n_base = (warp & 1) * 16;
+                    mtc = min(4, max(0, (mpad - m_base) / 8));
+                    ntc = min(2, max(0, (cur_nt + 7 - n_base) / 8));
+                }
+                else
+                {
+                    const int tm = MT > 8 ? 4 : MT > 4 ? 2 : 1;
+                    m_base = (warp & 3) * tm * 8; n_base = (warp >> 2) * 8;
+                    mtc = min(tm, max(0, (mpad - m_base) / 8));
+                    ntc = cur_nt > n_base ? 1 : 0;
+                }
+                active = mtc > 0 && ntc > 0;
+                if (active)
+                {
 #pragma unroll
                     for (int mt = 0; mt < 4; ++mt)
                     {
@@ -360,7 +384,11 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                         cfull[q] = v;
                     }
                 }
-                else
+            }
+            else
+            {
+                active = (cur_m > tx) && (ty * CPT < cur_nt);
+                if (active)
                 {
 #pragma unroll
                     for (int i2 = 0; i2 < 8; ++i2)
@@ -377,67 +405,96 @@ __device__ __forceinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb,
                         cfull[j] = v;
                     }
                 }
-            }
-            const int s = ci % nst;
-            mbar_wait(bars + s, (full_bits >> s) & 1u);
-            full_bits ^= 1u << s;
-            const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes);
-            const T* Bs = As + KC * cur_ld;
-            if constexpr (kDouble)
-            {
-                if (mtc > 0 && ntc > 0)
+                else
                 {
-                    const double* Ap = As + lk * cur_ld + m_base + lr;
-                    const double* Bp = Bs + (n_base + lr) * BLD + lk;
 #pragma unroll
-                    for (int k4 = 0; k4 < KC; k4 += 4)
-                    {
-                        double a[4], b[2];
-#pragma unroll
-                        for (int mt = 0; mt < 4; ++mt) a[mt] = mt < mtc ? Ap[k4 * cur_ld + mt * 8] : 0.0;
-                        b[0] = Bp[k4];
-                        b[1] = ntc > 1 ? Bp[8 * BLD + k4] : 0.0;
-#pragma unroll
-                        for (int mt = 0; mt < 4; ++mt)
-                            if (mt < mtc)
-                            {
-                                dmma884c(racc[(mt * 2) * 2], racc[(mt * 2) * 2 + 1], a[mt], b[0]);
-                                if (ntc > 1) dmma884c(racc[(mt * 2 + 1) * 2], racc[(mt * 2 + 1) * 2 + 1], a[mt], b[1]);
-                            }
-                    }
+                    for (int i2 = 0; i2 < 8; ++i2) rf8[i2] = 0xffff;
                 }
             }
-            else
+            const bool warp_active = __any_sync(PSM_FULL, active);
+            for (int j = 0; j < cnt; ++j, ++ci)
             {
-                const int mi = min(8, (cur_m - tx + 31) / 32);  // row slices of this lane that exist
-                if (mi > 0 && ty * CPT < cur_nt)
+                if (tid == 0 && ci + LA < nitems) produce(ci + LA);
+                const int s = ci & smask;
+                mbar_wait(bars + s, (full_bits >> s) & 1u);
+                full_bits ^= 1u << s;
+                if (warp_active)
                 {
+                    const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes);
+                    const T* Bs = As + KC * cur_ld;
+                    if constexpr (kDouble)
+                    {
+                        const double* Ap = As + lk * cur_ld + m_base + lr;
+                        const double* Bp = Bs + (n_base + lr) * BLD + lk;
+                        if (small)
+                        {
+#pragma unroll
+                            for (int k4 = 0; k4 < KC; k4 += 4)
+                            {
+                                const double b = Bp[k4];
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt)
+                                    if (mt < mtc)
+                                    {
+                                        const double a = Ap[k4 * cur_ld + mt * 8];
+                                        if ((k4 >> 2) & 1) dmma884c(racc[(mt * 2 + 1) * 2], racc[(mt * 2 + 1) * 2 + 1], a, b);
+                                        else dmma884c(racc[(mt * 2) * 2], racc[(mt * 2) * 2 + 1], a, b);
+                                    }
+                            }
+                        }
+                        else
+                        {
+#pragma unroll
+                            for (int k4 = 0; k4 < KC; k4 += 4)
+                            {
+                                double a[4], b[2];
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt) a[mt] = mt < mtc ? Ap[k4 * cur_ld + mt * 8] : 0.0;
+                                b[0] = Bp[k4];
+                                b[1] = ntc > 1 ? Bp[8 * BLD + k4] : 0.0;
+#pragma unroll
+                                for (int mt = 0; mt < 4; ++mt)
+                                    if (mt < mtc)
+                                    {
+                                        dmma884c(racc[(mt * 2) * 2], racc[(mt * 2) * 2 + 1], a[mt], b[0]);
+                                        if (ntc > 1) dmma884c(racc[(mt * 2 + 1) * 2], racc[(mt * 2 + 1) * 2 + 1], a[mt], b[1]);
+                                    }
+                            }
+                        }
+                    }
+                    else
+                    {
+                        const int mi = min(8, (cur_m - tx + 31) / 32);  // row slices of this lane that exist
+                        if (active)
+                        {
 #pragma unroll 4
-                    for (int kk = 0; kk < KC; ++kk)
-                    {
-                        T bv[CPT];
-#pragma unroll
-                        for (int j = 0; j < CPT; ++j) bv[j] = Bs[(ty * CPT + j) * BLD + kk];
-#pragma unroll
-                        for (int i2 = 0; i2 < 8; ++i2)
-                            if (i2 < mi)
+                            for (int kk = 0; kk < KC; ++kk)
                             {
-                                const T av = As[kk * cur_ld + tx + 32 * i2];
+                                T bv[CPT];
 #pragma unroll
-                                for (int j = 0; j < CPT; ++j) fma_acc(racc[i2 * CPT + j], av, bv[j]);
+                                for (int j2 = 0; j2 < CPT; ++j2) bv[j2] = Bs[(ty * CPT + j2) * BLD + kk];
+#pragma unroll
+                                for (int i2 = 0; i2 < 8; ++i2)
+                                    if (i2 < mi)
+                                    {
+                                        const T av = As[kk * cur_ld + tx + 32 * i2];
+#pragma unroll
+                                        for (int j2 = 0; j2 < CPT; ++j2) fma_acc(racc[i2 * CPT + j2], av, bv[j2]);
+                                    }
                             }
+                        }
                     }
+                    __syncwarp();
                 }
+                if (lane == 0) mbar_arrive(bars + NSLOT + s);
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bars + NSLOT + s);
         }
-        if (cur_pair >= 0) flush();
+        if (have_prev) flush();
         // every release must be matched by a wait of the producer, so the barrier bits stay in step
         if (tid == 0)
             for (int j = max(0, nitems - nst); j < nitems; ++j)
             {
-                const int s = j % nst;
+                const int s = j & smask;
                 mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u);
                 empty_bits ^= 1u << s;
             }
@@ -565,7 +622,7 @@ __device__ __forceinline__ void diag_densify(int nb, const GetrfTask<T>& G, cons
 }
 
 template <class T>
-__device__ __forceinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, const PanelTask<T>& Q, const DenseOp<T>& Dn, const DiagDense<T>& DD,
+__device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, const PanelTask<T>& Q, const DenseOp<T>& Dn, const DiagDense<T>& DD,
                                                   int r0, CpState& st)
 {
     typedef CpLayout<T> Lay;
@@ -698,13 +755,15 @@ __device__ __forceinline__ void panel_compact_cta(unsigned char* smem_raw, int n
             T x[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) x[c] = X[(Jcur * 16 + c) * LDX + tid];
+            // right-looking inside the 16 columns: the 15-k updates after a division are independent (same operations on
+            // every entry, in the same order, as the column-by-column form)
 #pragma unroll
-            for (int c = 0; c < 16; ++c)
+            for (int k = 0; k < 16; ++k)
             {
+                if (!gessm) x[k] = vdiv(x[k], clamp_pivot(Tjj[k * BLD + k]));
 #pragma unroll
-                for (int k = 0; k < 16; ++k)
-                    if (k < c) fnma(x[c], x[k], Tjj[c * BLD + k]);
-                if (!gessm) x[c] = vdiv(x[c], clamp_pivot(Tjj[c * BLD + c]));
+                for (int c = 0; c < 16; ++c)
+                    if (c > k) fnma(x[c], x[k], Tjj[c * BLD + k]);
             }
 #pragma unroll
             for (int c = 0; c < 16; ++c) X[(Jcur * 16 + c) * LDX + tid] = x[c];

@@ -267,73 +267,116 @@ panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_pe
 // level needs two block barriers.
 //   smem = 4 * nb * sizeof(T)
 // ------------------------------------------------------------------------------------------------
+// The level loop is software-pipelined so that a level costs ONE block barrier: while warps 1.. apply level l's
+// rank-1 update to the trailing rows / columns, warp 0 applies it to row and column `ln` (the next level that has
+// work) first and then already prepares that level (divides L(:,ln) by the clamped pivot, scatters it and U(ln,:)
+// into the other pair of dense vectors).  Every entry still sees the same operations in the same order.
 template <class T, int THREADS>
 __device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, const u16* lidx, T* uval, const u32* uptr, const u16* uidx, T* buf)
 {
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
     constexpr int NW = THREADS / PSM_WARP;
-    int prev_level = -1, step = 0;
-    for (int level = 0; level < nb; ++level)
-    {
-        const u32 u0 = col_begin(uptr, level), u1 = uptr[level + 1];
-        if (u0 == u1) continue;  // padded row beyond n (pangulu_platform_0100000.c:74-77)
-        const u32 l0 = col_begin(lptr, level), l1 = lptr[level + 1];
-        if (l0 == l1 && u1 - u0 == 1) continue;  // only the pivot: nothing to scale, nothing to update
-        const int par = (step++) & 1;  // parity of the processed-level count: skipped rows do not flip it
+    // next level >= from that has something to do: a non-empty U row (rows beyond n are padding,
+    // pangulu_platform_0100000.c:74-77) and more than the pivot alone
+    auto next_level = [&](int from) {
+        for (int l = from; l < nb; ++l)
+        {
+            const u32 u0 = col_begin(uptr, l), u1 = uptr[l + 1];
+            if (u0 == u1) continue;
+            if (col_begin(lptr, l) == lptr[l + 1] && u1 - u0 == 1) continue;
+            return l;
+        }
+        return nb;
+    };
+    // warp 0: scale L(:,l), scatter it and U(l,:) into the vectors of parity `par`, after clearing what level `old`
+    // left there
+    auto prepare = [&](int l, int par, int old) {
         T* lcol = buf + (size_t)(par * 2) * nb;
         T* urow = lcol + nb;
+        if (old >= 0)
+        {
+            for (u32 e = col_begin(lptr, old) + lane; e < lptr[old + 1]; e += PSM_WARP) lcol[lidx[e]] = zero<T>();
+            for (u32 e = col_begin(uptr, old) + 1 + lane; e < uptr[old + 1]; e += PSM_WARP) urow[uidx[e]] = zero<T>();
+            __syncwarp();
+        }
+        const u32 u0 = col_begin(uptr, l), u1 = uptr[l + 1];
         const T piv = clamp_pivot(uval[u0]);
-        for (u32 e = l0 + tid; e < l1; e += THREADS)
+        for (u32 e = col_begin(lptr, l) + lane; e < lptr[l + 1]; e += PSM_WARP)
         {
             const T v = vdiv(lval[e], piv);
             lval[e] = v;
             lcol[lidx[e]] = v;
         }
-        for (u32 e = u0 + 1 + tid; e < u1; e += THREADS) urow[uidx[e]] = uval[e];
-        // clear the OTHER parity's vectors (used by prev_level; all its readers passed the barrier
-        // that ended that level)
-        if (prev_level >= 0)
+        for (u32 e = u0 + 1 + lane; e < u1; e += PSM_WARP) urow[uidx[e]] = uval[e];
+    };
+    auto update_row = [&](int r, const T* lcol, const T* urow) {   // U(r,:) -= L(r,l) U(l,:)
+        const T lr = lcol[r];
+        const u32 r0 = col_begin(uptr, r), r1 = uptr[r + 1];
+        for (u32 q = r0 + lane; q < r1; q += PSM_WARP)
         {
-            T* plcol = buf + (size_t)((par ^ 1) * 2) * nb;
-            T* purow = plcol + nb;
-            const u32 pl0 = col_begin(lptr, prev_level), pl1 = lptr[prev_level + 1];
-            const u32 pu0 = col_begin(uptr, prev_level), pu1 = uptr[prev_level + 1];
-            for (u32 e = pl0 + tid; e < pl1; e += THREADS) plcol[lidx[e]] = zero<T>();
-            for (u32 e = pu0 + 1 + tid; e < pu1; e += THREADS) purow[uidx[e]] = zero<T>();
+            T v = uval[q];
+            fnma(v, lr, urow[uidx[q]]);
+            uval[q] = v;
         }
-        __syncthreads();
-
-        const int nrow = (int)(l1 - l0), ncol = (int)(u1 - u0 - 1);
-        for (int it = warp; it < nrow + ncol; it += NW)
+    };
+    auto update_col = [&](int c, const T* lcol, const T* urow) {   // L(:,c) -= L(:,l) U(l,c)
+        const T uc = urow[c];
+        const u32 q0 = col_begin(lptr, c), q1 = lptr[c + 1];
+        for (u32 q = q0 + lane; q < q1; q += PSM_WARP)
         {
-            if (it < nrow)
+            T v = lval[q];
+            fnma(v, lcol[lidx[q]], uc);
+            lval[q] = v;
+        }
+    };
+
+    int level = next_level(0), prev_level = -1, par = 0;
+    if (level >= nb) return;
+    if (warp == 0) prepare(level, 0, -1);
+    __syncthreads();
+    while (level < nb)
+    {
+        const int ln = next_level(level + 1);
+        const T* lcol = buf + (size_t)(par * 2) * nb;
+        const T* urow = lcol + nb;
+        const u32 l0 = col_begin(lptr, level), l1 = lptr[level + 1];
+        const u32 u0 = col_begin(uptr, level), u1 = uptr[level + 1];
+        const int nrow = (int)(l1 - l0), ncol = (int)(u1 - u0 - 1);
+        if (warp == 0)
+        {
+            // critical path: row ln and column ln first (if level `level` touches them), then prepare level ln
+            if (ln < nb)
             {
-                const int r = lidx[l0 + it];
-                const T lr = lcol[r];
-                const u32 r0 = col_begin(uptr, r), r1 = uptr[r + 1];
-                for (u32 q = r0 + lane; q < r1; q += PSM_WARP)
-                {
-                    T v = uval[q];
-                    fnma(v, lr, urow[uidx[q]]);
-                    uval[q] = v;
-                }
+                bool hit = false;
+                for (u32 e = l0 + lane; e < l1 && !hit; e += PSM_WARP) hit = lidx[e] == ln;
+                if (__any_sync(PSM_FULL, hit)) update_row(ln, lcol, urow);
+                hit = false;
+                for (u32 e = u0 + 1 + lane; e < u1 && !hit; e += PSM_WARP) hit = uidx[e] == ln;
+                if (__any_sync(PSM_FULL, hit)) update_col(ln, lcol, urow);
+                __syncwarp();
+                prepare(ln, par ^ 1, prev_level);
             }
-            else
+        }
+        else
+        {
+            for (int it = warp - 1; it < nrow + ncol; it += NW - 1)
             {
-                const u32 eu = u0 + 1 + (it - nrow);
-                const int c = uidx[eu];
-                const T uc = urow[c];
-                const u32 q0 = col_begin(lptr, c), q1 = lptr[c + 1];
-                for (u32 q = q0 + lane; q < q1; q += PSM_WARP)
+                if (it < nrow)
                 {
-                    T v = lval[q];
-                    fnma(v, lcol[lidx[q]], uc);
-                    lval[q] = v;
+                    const int r = lidx[l0 + it];
+                    if (r != ln) update_row(r, lcol, urow);
+                }
+                else
+                {
+                    const int c = uidx[u0 + 1 + (it - nrow)];
+                    if (c != ln) update_col(c, lcol, urow);
                 }
             }
         }
         __syncthreads();
         prev_level = level;
+        level = ln;
+        par ^= 1;
     }
 }
 
