@@ -150,6 +150,12 @@ void *pangulu_sm100_plan_sync_base(pangulu_sm100_plan *plan, size_t *bytes);
 long long pangulu_sm100_plan_flag_offset(pangulu_sm100_plan *plan, const void *d_value);
 void pangulu_sm100_plan_expect_remote(pangulu_sm100_plan *plan, const void *d_value);
 void pangulu_sm100_plan_add_push(pangulu_sm100_plan *plan, const void *d_value_local, void *peer_value, void *peer_flag);
+/* compact dense operand copies (sm100_compact.cuh) across ranks: where the plan keeps them (one allocation, exported
+ * with pangulu_sm100_ipc_export), the byte offset of the copy of the block whose device value array is d_value (-1:
+ * none), and a push that also writes the owner's copy into the consumer's (peer_dense, peer-mapped; may be NULL) */
+void *pangulu_sm100_plan_dense_base(pangulu_sm100_plan *plan, size_t *bytes);
+long long pangulu_sm100_plan_dense_offset(pangulu_sm100_plan *plan, const void *d_value);
+void pangulu_sm100_plan_add_push2(pangulu_sm100_plan *plan, const void *d_value_local, void *peer_value, void *peer_flag, void *peer_dense);
 void pangulu_sm100_plan_commit(pangulu_sm100_plan *plan);
 void pangulu_sm100_plan_reset(pangulu_sm100_plan *plan);
 void pangulu_sm100_plan_launch(pangulu_sm100_plan *plan);

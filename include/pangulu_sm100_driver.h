@@ -83,9 +83,9 @@ void pangulu_sm100_driver_gstrf_enqueue(void *handle);
  * torch.distributed.all_gather_object), call connect_peer once per peer and commit.  pangulu_gstrf then needs a
  * host barrier (set_barrier).  Finished blocks travel GPU-to-GPU inside the factorisation kernel. */
 void pangulu_sm100_driver_set_barrier(void (*fn)(void));
-void pangulu_sm100_driver_ipc_handles(void *handle, unsigned char *out128);
+void pangulu_sm100_driver_ipc_handles(void *handle, unsigned char *out192);
 long long pangulu_sm100_driver_mirror_table(void *handle, long long *out, long long cap);
-long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *handles128, const long long *table, long long n);
+long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *handles192, const long long *table, long long n);
 void pangulu_sm100_driver_commit(void *handle);
 void pangulu_sm100_driver_gstrf_reset(void *handle);
 void pangulu_sm100_driver_gstrf_launch(void *handle);

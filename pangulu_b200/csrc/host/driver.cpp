@@ -119,6 +119,8 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     h->mode = (int)g_cfg.mode;
     h->rank = (int)g_cfg.rank;
     h->nproc = (int)g_cfg.nproc;
+    // several ranks: a peer may read any owned panel block through its compact dense copy
+    if (!g_cfg.host_only) pangulu_sm100_set_option("dense_all_panels", h->nproc > 1 ? 1 : 0);
 
     // one rank <-> one GPU: rank % device_count (src/pangulu.c:126-130)
     h->B.host_only = g_cfg.host_only != 0;
@@ -386,19 +388,24 @@ static void ensure_plan(Handle* h)
                                             h->sched.tasks.data());
 }
 
-// 128 bytes: CUDA IPC handles of this rank's block buffer and of its plan's synchronisation buffer
-void pangulu_sm100_driver_ipc_handles(void* handle, unsigned char* out128)
+// 192 bytes: CUDA IPC handles of this rank's block buffer, of its plan's synchronisation buffer and of the plan's
+// compact dense operand copies (zeros when the plan has none)
+void pangulu_sm100_driver_ipc_handles(void* handle, unsigned char* out192)
 {
     Handle* h = (Handle*)handle;
     ensure_plan(h);
-    pangulu_sm100_ipc_export(h->B.d_buf, out128);
+    memset(out192, 0, 192);
+    pangulu_sm100_ipc_export(h->B.d_buf, out192);
     size_t bytes = 0;
-    pangulu_sm100_ipc_export(pangulu_sm100_plan_sync_base(h->plan, &bytes), out128 + 64);
+    pangulu_sm100_ipc_export(pangulu_sm100_plan_sync_base(h->plan, &bytes), out192 + 64);
+    void* dense = pangulu_sm100_plan_dense_base(h->plan, &bytes);
+    if (dense && bytes) pangulu_sm100_ipc_export(dense, out192 + 128);
 }
 
-// One row of 5 int64 per remote block this rank mirrors AND reads: {brow, bcol, kind (0 off-diagonal, 1 lower half,
+// One row of 6 int64 per remote block this rank mirrors AND reads: {brow, bcol, kind (0 off-diagonal, 1 lower half,
 // 2 upper half of a diagonal block), byte offset of its value array in the block buffer, byte offset of its done flag
-// in the plan's synchronisation buffer}.  Also tells the plan that these blocks arrive from a peer.
+// in the plan's synchronisation buffer, byte offset of its compact dense copy in the plan's dense buffer or -1}.
+// Also tells the plan that these blocks arrive from a peer.
 long long pangulu_sm100_driver_mirror_table(void* handle, long long* out, long long cap)
 {
     Handle* h = (Handle*)handle;
@@ -417,12 +424,13 @@ long long pangulu_sm100_driver_mirror_table(void* handle, long long* out, long l
         }
         if (out && n < cap)
         {
-            long long* r = out + 5 * n;
+            long long* r = out + 6 * n;
             r[0] = s.brow_pos;
             r[1] = s.bcol_pos;
             r[2] = s.brow_pos != s.bcol_pos ? 0 : (s.is_upper ? 2 : 1);
             r[3] = (long long)((char*)s.d_value - B.d_buf);
             r[4] = flag;
+            r[5] = B.host_only ? -1 : pangulu_sm100_plan_dense_offset(h->plan, s.d_value);
         }
         ++n;
     }
@@ -435,17 +443,20 @@ long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* h
 {
     Handle* h = (Handle*)handle;
     BlockStore& B = h->B;
-    char *peer_buf = nullptr, *peer_sync = nullptr;
+    char *peer_buf = nullptr, *peer_sync = nullptr, *peer_dense = nullptr;
     if (!B.host_only)
     {
         ensure_plan(h);
         pangulu_sm100_ipc_open(handles128, (void**)&peer_buf);
         pangulu_sm100_ipc_open(handles128 + 64, (void**)&peer_sync);
+        bool any_dense = false;
+        for (long long i = 0; i < n; ++i) any_dense = any_dense || table[6 * i + 5] >= 0;
+        if (any_dense) pangulu_sm100_ipc_open(handles128 + 128, (void**)&peer_dense);
     }
     long long made = 0;
     for (long long i = 0; i < n; ++i)
     {
-        const long long* r = table + 5 * i;
+        const long long* r = table + 6 * i;
         const eidx brow = (eidx)r[0], bcol = (eidx)r[1];
         if (B.owner(brow, bcol) != B.rank) continue;
         int64_t slot = -1;
@@ -464,7 +475,7 @@ long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* h
             fprintf(stderr, "[PanguLU ERROR] peer asks for block (%u,%u) that rank %d owns but does not hold\n", brow, bcol, B.rank);
             exit(EXIT_FAILURE);
         }
-        if (!B.host_only) pangulu_sm100_plan_add_push(h->plan, B.slots[slot].d_value, peer_buf + r[3], peer_sync + r[4]);
+        if (!B.host_only) pangulu_sm100_plan_add_push2(h->plan, B.slots[slot].d_value, peer_buf + r[3], peer_sync + r[4], r[5] >= 0 ? peer_dense + r[5] : nullptr);
         ++made;
     }
     return made;

@@ -63,6 +63,7 @@ struct Options
     long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
     long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
+    long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -328,17 +329,17 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             const bool tile_ok = nb >= 32 && nb <= 256 && mode != 1;
             const double thr = (double)g.opt.dense_threshold / 1000.0;
             const double nb4thr2 = thr * thr * (double)nb * nb * (double)nb * nb;
-            // compact path (plans only): both operands are owned blocks (a mirrored block of another rank has no compact
-            // copy on this rank) and the pair is not too sparse
+            // compact path (plans only): both operands have a compact dense copy.  Whether a block gets one depends on
+            // its pattern alone (density), so every rank that holds the block -- its owner and the ranks that mirror it --
+            // decides the same way
             const bool compact_ok = reg && g.opt.compact != 0 && nb % 16 == 0 && nb >= 32 && nb <= 256;
-            const double cthr = (double)g.opt.compact_threshold / 1000.0;
-            const double nb4cthr2 = cthr * cthr * (double)nb * nb * (double)nb * nb;
+            const double cmin = (double)g.opt.compact_threshold / 1000.0 * (double)nb * nb;
             for (size_t k = 0; k < nrun; ++k)
             {
                 order[k] = k;
                 const pangulu_task_t& t = tasks[i + k];
                 const double na = slot_nnz(nb, t.op1), nbn = slot_nnz(nb, t.op2);
-                if (compact_ok && t.op1->bin_id == 0 && t.op2->bin_id == 0 && na * nbn >= nb4cthr2) cls[k] = 2;
+                if (compact_ok && na >= cmin && nbn >= cmin) cls[k] = 2;
                 else cls[k] = (tile_ok && (mode == 2 || na * nbn >= nb4thr2)) ? 0 : 1;
             }
             auto key = [&](size_t k) -> const void* {
@@ -881,6 +882,8 @@ struct pangulu_sm100_plan
     void* dense_meta = nullptr;  // row / column lists and inverse maps
     std::vector<const void*> op_val;  // per compact copy: device value array of the block it mirrors (sync id key)
     void* diag_dense_buf = nullptr;   // dense triangular copies of diagonal blocks (compact panel path)
+    std::unordered_map<const void*, size_t> dense_of_val;  // device value array -> compact copy index
+    size_t dense_total_bytes = 0;
     // persistent executor
     bool mega = false;
     void* mega_buf = nullptr;
@@ -1246,6 +1249,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "compact")) return &g.opt.compact;
     if (!strcmp(key, "compact_threshold")) return &g.opt.compact_threshold;
     if (!strcmp(key, "cpanel")) return &g.opt.cpanel;
+    if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)
@@ -1294,6 +1298,13 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     }
     pl->wave_step.push_back(pl->P.steps.size());
     Program& P = pl->P;
+    if (g.opt.dense_all_panels != 0 && g.opt.compact != 0 && nb % 16 == 0 && nb >= 32 && nb <= 256)
+    {
+        // several ranks: a peer may read an owned block through its compact copy even if no local update does
+        const double cmin = (double)g.opt.compact_threshold / 1000.0 * (double)nb * nb;
+        for (const pangulu_storage_slot_t* sl : P.panel_slot)
+            if ((double)slot_nnz(nb, sl) >= cmin) pl->reg.get(sl, sl->brow_pos < sl->bcol_pos);
+    }
     // compact dense copies: allocate, zero, describe; tell every panel task which copy (if any) its block feeds
     std::vector<DenseOp<T>> ops(pl->reg.entries.size());
     if (!ops.empty())
@@ -1316,7 +1327,9 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             o.kmask = e.kmask;
             o.pre = o.inv + pl->reg.nb;
             pl->op_val.push_back(e.slot->d_value);
+            pl->dense_of_val.emplace(e.slot->d_value, i);
         }
+        pl->dense_total_bytes = R.dense_total * sizeof(T);
         for (size_t i = 0; i < P.panel.size(); ++i) P.panel[i].dense = R.find(P.panel_slot[i]);
     }
     // compact panel path: panel tasks whose block has a compact copy and whose diagonal block is factored on this rank
@@ -1528,14 +1541,42 @@ void pangulu_sm100_plan_expect_remote(pangulu_sm100_plan* pl, const void* d_valu
     auto it = pl->ids.find(d_value);
     if (it != pl->ids.end()) pl->h_done_init[it->second] = 0;
 }
-void pangulu_sm100_plan_add_push(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag)
+void pangulu_sm100_plan_add_push2(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag, void* peer_dense)
 {
     auto it = pl->ids.find(d_value_local);
     if (it == pl->ids.end()) return;  // the block is not produced or referenced by this plan
     MegaPush<T> e;
     e.peer_val = (T*)peer_value;
     e.peer_flag = (int*)peer_flag;
+    e.peer_dense = nullptr;
+    e.src_dense = nullptr;
+    e.dense_count = 0;
+    if (peer_dense)
+    {
+        auto d = pl->dense_of_val.find(d_value_local);
+        if (d == pl->dense_of_val.end()) fatal(__FILE__, __LINE__, "a peer reads the compact copy of a block that has none here (set option dense_all_panels on every rank)", nullptr);
+        const DenseReg::Entry& en = pl->reg.entries[d->second];
+        e.peer_dense = (T*)peer_dense;
+        e.src_dense = (const T*)pl->dense_buf + en.dense_off;
+        e.dense_count = en.dense_len;
+    }
     pl->h_push[it->second].push_back(e);
+}
+void pangulu_sm100_plan_add_push(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag)
+{
+    pangulu_sm100_plan_add_push2(pl, d_value_local, peer_value, peer_flag, nullptr);
+}
+void* pangulu_sm100_plan_dense_base(pangulu_sm100_plan* pl, size_t* bytes)
+{
+    if (bytes) *bytes = pl ? pl->dense_total_bytes : 0;
+    return pl ? pl->dense_buf : nullptr;
+}
+long long pangulu_sm100_plan_dense_offset(pangulu_sm100_plan* pl, const void* d_value)
+{
+    if (!pl) return -1;
+    auto d = pl->dense_of_val.find(d_value);
+    if (d == pl->dense_of_val.end()) return -1;
+    return (long long)(pl->reg.entries[d->second].dense_off * sizeof(T));
 }
 void pangulu_sm100_plan_commit(pangulu_sm100_plan* pl)
 {

@@ -1142,7 +1142,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 // running CTA, so the spin waits cannot deadlock.
 // ================================================================================================
 struct MegaTask { int kind, a, b, c; };
-template <class T> struct MegaPush { T* peer_val; int* peer_flag; };
+template <class T> struct MegaPush { T* peer_val; int* peer_flag; T* peer_dense; const T* src_dense; size_t dense_count; };
 enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6, MEGA_CPANEL = 7 };
 
 template <class T>
@@ -1218,6 +1218,14 @@ __device__ __forceinline__ void push_block(const int* push_ptr, const MegaPush<T
     {
         T* dst = pushes[e].peer_val;
         for (u32 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        if (pushes[e].peer_dense)
+        {
+            // the consumer reads the block through its compact dense copy: same layout on both ranks
+            T* dd = pushes[e].peer_dense;
+            const T* sd = pushes[e].src_dense;
+            const size_t nd = pushes[e].dense_count;
+            for (size_t i = threadIdx.x; i < nd; i += blockDim.x) dd[i] = sd[i];
+        }
     }
     __threadfence_system();
     __syncthreads();

@@ -121,14 +121,14 @@ class PanguLU:
 
     # -- multi-GPU wiring ---------------------------------------------------------------------------------
     def mirror_table(self) -> np.ndarray:
-        """int64[n, 5]: remote blocks this rank reads (brow, bcol, kind, value offset, flag offset)."""
+        """int64[n, 6]: remote blocks this rank reads (brow, bcol, kind, value offset, flag offset, dense-copy offset)."""
         n = int(self.L.pangulu_sm100_driver_mirror_table(self._h, None, 0))
-        out = np.zeros((max(n, 1), 5), dtype=np.int64)
+        out = np.zeros((max(n, 1), 6), dtype=np.int64)
         self.L.pangulu_sm100_driver_mirror_table(self._h, out.ctypes.data, n)
         return out[:n]
 
     def ipc_handles(self) -> bytes:
-        buf = (C.c_ubyte * 128)()
+        buf = (C.c_ubyte * 192)()
         self.L.pangulu_sm100_driver_ipc_handles(self._h, buf)
         return bytes(buf)
 
@@ -139,7 +139,7 @@ class PanguLU:
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         table = self.mirror_table()
-        handles = self.ipc_handles() if not self._host_only else bytes(128)
+        handles = self.ipc_handles() if not self._host_only else bytes(192)
         gathered = [None] * world
         dist.all_gather_object(gathered, (handles, table), group=group)
         made = 0
@@ -147,7 +147,7 @@ class PanguLU:
             if r == rank or len(tb) == 0:
                 continue
             tb = np.ascontiguousarray(tb, dtype=np.int64)
-            hb = (C.c_ubyte * 128).from_buffer_copy(hd)
+            hb = (C.c_ubyte * 192).from_buffer_copy(hd)
             made += int(self.L.pangulu_sm100_driver_connect_peer(self._h, hb, tb.ctypes.data, len(tb)))
         self.L.pangulu_sm100_driver_commit(self._h)
         self._barrier_cb = C.CFUNCTYPE(None)(lambda: dist.barrier(group))
