@@ -61,7 +61,8 @@ struct Options
     long long trace = 0;        // persistent executor: record per-task fetch/start/end timestamps (pangulu_sm100_plan_trace)
     long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
     long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
-    long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path
+    long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path ...
+    long long compact_block_threshold = 1;  // ... if both blocks have nnz/nb^2 >= this (per mille): the block-level rule decides who gets a compact copy
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
 };
@@ -333,13 +334,15 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             // its pattern alone (density), so every rank that holds the block -- its owner and the ranks that mirror it --
             // decides the same way
             const bool compact_ok = reg && g.opt.compact != 0 && nb % 16 == 0 && nb >= 32 && nb <= 256;
-            const double cmin = (double)g.opt.compact_threshold / 1000.0 * (double)nb * nb;
+            const double cmin = (double)g.opt.compact_block_threshold / 1000.0 * (double)nb * nb;
+            const double cthr = (double)g.opt.compact_threshold / 1000.0;
+            const double nb4cthr2 = cthr * cthr * (double)nb * nb * (double)nb * nb;
             for (size_t k = 0; k < nrun; ++k)
             {
                 order[k] = k;
                 const pangulu_task_t& t = tasks[i + k];
                 const double na = slot_nnz(nb, t.op1), nbn = slot_nnz(nb, t.op2);
-                if (compact_ok && na >= cmin && nbn >= cmin) cls[k] = 2;
+                if (compact_ok && na >= cmin && nbn >= cmin && na * nbn >= nb4cthr2) cls[k] = 2;
                 else cls[k] = (tile_ok && (mode == 2 || na * nbn >= nb4thr2)) ? 0 : 1;
             }
             auto key = [&](size_t k) -> const void* {
@@ -1248,6 +1251,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "trace")) return &g.opt.trace;
     if (!strcmp(key, "compact")) return &g.opt.compact;
     if (!strcmp(key, "compact_threshold")) return &g.opt.compact_threshold;
+    if (!strcmp(key, "compact_block_threshold")) return &g.opt.compact_block_threshold;
     if (!strcmp(key, "cpanel")) return &g.opt.cpanel;
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     return nullptr;
@@ -1301,7 +1305,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     if (g.opt.dense_all_panels != 0 && g.opt.compact != 0 && nb % 16 == 0 && nb >= 32 && nb <= 256)
     {
         // several ranks: a peer may read an owned block through its compact copy even if no local update does
-        const double cmin = (double)g.opt.compact_threshold / 1000.0 * (double)nb * nb;
+        const double cmin = (double)g.opt.compact_block_threshold / 1000.0 * (double)nb * nb;
         for (const pangulu_storage_slot_t* sl : P.panel_slot)
             if ((double)slot_nnz(nb, sl) >= cmin) pl->reg.get(sl, sl->brow_pos < sl->bcol_pos);
     }

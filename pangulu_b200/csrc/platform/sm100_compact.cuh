@@ -601,7 +601,7 @@ struct CpLayout
     static constexpr size_t x_bytes = (size_t)256 * PSM_CP_LDX * sizeof(T);
     static constexpr size_t sub_bytes = (size_t)16 * PSM_CT_BLD * sizeof(T);     // one 16 x 16 sub-block of Tm
     static constexpr size_t tbuf_bytes = 16 * sub_bytes;                            // one column block (all K)
-    static constexpr size_t total = x_bytes + 2 * tbuf_bytes + 64;
+    static constexpr size_t total = x_bytes + 2 * tbuf_bytes + 4 * (260 + 64) + 2 * 256 + 64;  // + pointer / prefix / inverse-map staging
 };
 
 struct CpState { u32 bits = 0; bool armed = false; };
@@ -669,23 +669,116 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     int Jcur = kmask ? (__ffs(kmask) - 1) : -1;
     int par = 0;
     if (tid == 0 && Jcur >= 0) issue(Jcur, 0);
+    // Gather (and, at the end, scatter) run as FLAT loops over the slice's entries with the block's pointer array and
+    // inverse row map staged in shared memory: many independent loads in flight instead of a chain of dependent ones
+    // per column.
+    u32* sptr = reinterpret_cast<u32*>(smem_raw + Lay::x_bytes + 2 * Lay::tbuf_bytes);   // [nb+1] column pointers (TSTRF) / [65] slice prefix (GESSM)
+    u32* sbeg = sptr + 260;                                                               // GESSM: first entry of each slice column
+    u16* sinv = reinterpret_cast<u16*>(sbeg + 64);                                        // TSTRF: [nb] row -> compact row
+    u32 nflat = 0;
     if (gessm)
     {
-        for (int s = warp; s < nrows; s += 16)
+        if (warp == 0)
         {
-            const int c = Dn.list[r0 + s];
-            for (u32 e = col_begin(B.ptr, c) + lane; e < B.ptr[c + 1]; e += PSM_WARP) X[(int)B.idx[e] * LDX + s] = B.val[e];
+            u32 run = 0;
+            for (int base = 0; base < R; base += PSM_WARP)
+            {
+                const int sidx = base + lane;
+                u32 b = 0, len = 0;
+                if (sidx < nrows)
+                {
+                    const int c = Dn.list[r0 + sidx];
+                    b = col_begin(B.ptr, c);
+                    len = B.ptr[c + 1] - b;
+                }
+                u32 incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const u32 v = __shfl_up_sync(PSM_FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                sptr[sidx] = run + incl - len;
+                sbeg[sidx] = b;
+                run += __shfl_sync(PSM_FULL, incl, 31);
+            }
+            if (lane == 0) sptr[R] = run;
         }
     }
     else
     {
-        for (int k = warp; k < nb; k += 16)
-            for (u32 e = col_begin(B.ptr, k) + lane; e < B.ptr[k + 1]; e += PSM_WARP)
-            {
-                const int s = (int)Dn.inv[B.idx[e]] - r0;
-                if (s >= 0 && s < R) X[k * LDX + s] = B.val[e];
-            }
+        for (int i = tid; i <= nb; i += 512) sptr[i] = i == 0 ? 0u : B.ptr[i];
+        for (int i = tid; i < nb; i += 512) sinv[i] = Dn.inv[i];
     }
+    __syncthreads();
+    nflat = gessm ? sptr[R] : sptr[nb];
+    // Each warp walks a contiguous 1/16 of the flat entry range, four 32-entry groups at a time; the column (TSTRF) or
+    // slice column (GESSM) of an entry is found by advancing a cursor over the staged pointers (monotone per lane).
+    const int nseg = gessm ? R : nb;
+    const u32 per_warp = (nflat + 15) / 16;
+    const u32 jb = min(nflat, (u32)warp * per_warp), je = min(nflat, jb + per_warp);
+    int seg0 = 0;
+    {
+        int lo = 0, hi = nseg;   // largest segment with sptr[seg] <= jb
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sptr[mid] <= jb) lo = mid; else hi = mid; }
+        seg0 = lo;
+    }
+    // pass = 0: X <- block values;  pass = 1: block values <- X
+    auto sweep = [&](int pass) {
+        int seg = seg0;
+        for (u32 j0 = jb + lane; j0 < je; j0 += 4 * PSM_WARP)
+        {
+            u32 e[4];
+            int kk[4], sl[4];
+            u16 ri[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const u32 j = j0 + u * PSM_WARP;
+                kk[u] = -1;
+                if (j < je)
+                {
+                    while (j >= sptr[seg + 1]) ++seg;
+                    kk[u] = seg;
+                    e[u] = gessm ? sbeg[seg] + (j - sptr[seg]) : j;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (kk[u] >= 0) ri[u] = B.idx[e[u]];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                sl[u] = -1;
+                if (kk[u] >= 0)
+                {
+                    if (gessm) { sl[u] = kk[u]; kk[u] = ri[u]; }   // segment = slice column, entry row = k
+                    else
+                    {
+                        const int sc = (int)sinv[ri[u]] - r0;
+                        sl[u] = (sc >= 0 && sc < R) ? sc : -1;
+                    }
+                }
+            }
+            if (pass == 0)
+            {
+                T v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (sl[u] >= 0) v[u] = B.val[e[u]];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (sl[u] >= 0) X[kk[u] * LDX + sl[u]] = v[u];
+            }
+            else
+            {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (sl[u] >= 0) B.val[e[u]] = X[kk[u] * LDX + sl[u]];
+            }
+        }
+    };
+    sweep(0);
     __syncthreads();
 
     const int lr = lane / 4, lk = lane % 4, lc = (lane % 4) * 2;
@@ -775,34 +868,24 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     st.bits = bits;
 
     // ---- write back: CSC values and the compact dense copy
+    sweep(1);
     if (gessm)
     {
-        for (int s = warp; s < nrows; s += 16)
-        {
-            const int c = Dn.list[r0 + s];
-            for (u32 e = col_begin(B.ptr, c) + lane; e < B.ptr[c + 1]; e += PSM_WARP) B.val[e] = X[(int)B.idx[e] * LDX + s];
-        }
         // dense copy (B-operand layout): (k, c') at ((k/16) n' + c') 20 + k%16 -- 16 consecutive k are contiguous
         const int nchunk = nb / 16;
         for (int i = tid; i < nchunk * nrows * 16; i += 512)
         {
-            const int kk = i % 16, s = (i / 16) % nrows, ch = i / (16 * nrows);
-            if ((kmask >> ch) & 1u) Dn.dense[((size_t)ch * Dn.cnt + r0 + s) * BLD + kk] = X[(ch * 16 + kk) * LDX + s];
+            const int kk = i % 16, s2 = (i / 16) % nrows, ch = i / (16 * nrows);
+            if ((kmask >> ch) & 1u) Dn.dense[((size_t)ch * Dn.cnt + r0 + s2) * BLD + kk] = X[(ch * 16 + kk) * LDX + s2];
         }
     }
     else
     {
-        for (int k = warp; k < nb; k += 16)
-            for (u32 e = col_begin(B.ptr, k) + lane; e < B.ptr[k + 1]; e += PSM_WARP)
-            {
-                const int s = (int)Dn.inv[B.idx[e]] - r0;
-                if (s >= 0 && s < R) B.val[e] = X[k * LDX + s];
-            }
         // dense copy (A-operand layout): (r', k) at k ld + r'
         for (int i = tid; i < nb * nrows; i += 512)
         {
-            const int s = i % nrows, k = i / nrows;
-            if ((kmask >> (k / 16)) & 1u) Dn.dense[(size_t)k * Dn.ld + r0 + s] = X[k * LDX + s];
+            const int s2 = i % nrows, k = i / nrows;
+            if ((kmask >> (k / 16)) & 1u) Dn.dense[(size_t)k * Dn.ld + r0 + s2] = X[k * LDX + s2];
         }
     }
     __syncthreads();

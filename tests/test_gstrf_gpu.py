@@ -159,6 +159,7 @@ def test_gstrf_compact_dense_path(vtype, threshold, executor):
     L = _lib.load(vtype)
     L.pangulu_sm100_set_option(b"compact", 1)
     L.pangulu_sm100_set_option(b"compact_threshold", threshold)
+    L.pangulu_sm100_set_option(b"compact_block_threshold", 0 if threshold == 0 else 1)
     L.pangulu_sm100_set_option(b"executor", executor)
     s = PanguLU(A, nb=nb, mode=1)
     try:
@@ -181,5 +182,6 @@ def test_gstrf_compact_dense_path(vtype, threshold, executor):
         assert resid <= (1e-4 if "32" in vtype else 1e-12)
     finally:
         L.pangulu_sm100_set_option(b"compact_threshold", 10)
+        L.pangulu_sm100_set_option(b"compact_block_threshold", 1)
         L.pangulu_sm100_set_option(b"executor", 1)
         s.finalize()
