@@ -34,7 +34,11 @@ if ROOT not in sys.path:
 
 METRIC = "gstrf_gflops"
 UNIT = "GFLOP/s"
-NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 / FP64-tensor nominal peak (no measured FP64 number in MEASURED_PEAKS.json)
+NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 / FP64-tensor nominal peak
+# MEASURED_PEAKS.json carries HBM and bf16 numbers only; the FP64 tensor (DMMA.8x8x4) peak was measured on this pool with
+# scripts/micro/dmma_bench.cu (profiles/r01_dmma_microbench.txt): 37.0 TFLOP/s at 1965 MHz, 16.1 cycles per DMMA per SM sub-partition
+MEASURED_DMMA_TFLOPS = 37.0
+TASK_KINDS = ["ssssm_tile", "ssssm_sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel_sparse", "ssssm_compact", "panel_compact"]
 
 
 def parse_args():
@@ -48,6 +52,8 @@ def parse_args():
     ap.add_argument("--ref-size", type=int, default=32, help="grid size of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--abi-e2e", action="store_true", help="also time the per-wave hybrid_batched path with host task arrays")
+    ap.add_argument("--no-classes", action="store_true", help="skip the traced run that attributes device time to kernel classes")
     return ap.parse_args()
 
 
@@ -254,7 +260,9 @@ def run_ours(a):
     clocks = sampler.stop()
     class_ms = [L.pangulu_sm100_stats_ms(c) / a.steps for c in range(6)]
     class_launches = [L.pangulu_sm100_stats_launches(c) / a.steps for c in range(6)]
-    launches = int(sum(class_launches[:5]))
+    launches = int(sum(class_launches[:5])) + int(sum(L.pangulu_sm100_stats_launches(c) for c in (7, 8)) / a.steps)
+    mega_ms = L.pangulu_sm100_stats_ms(6) / a.steps              # (read here: the e2e runs below launch the same kernel again)
+    mega_launches = L.pangulu_sm100_stats_launches(6) / a.steps
     L.pangulu_sm100_set_option(b"profile", 0)
     ms = sum(times) / len(times)
     value = flop / (ms * 1e-3) / 1e9
@@ -267,22 +275,35 @@ def run_ours(a):
     # ---- e2e: reference-facing call path with host buffers --------------------------------------------------
     e2e = None
     if not a.no_e2e and world == 1:
-        s.set_mode(0)
+        # pangulu_gstrf() on HOST block buffers (pinned): upload the value region, run the resident plan, download the
+        # finished factors -- what a PanguLU user sees from the call
+        s.set_mode(2)
         et = []
         for it in range(1 + max(1, a.steps)):
             s.reset_values(False)          # host block buffers <- A (untimed)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            s.gstrf()                      # H2D values + per-wave hybrid_batched(host tasks) + D2H factors
+            s.gstrf()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
             if it >= 1:
                 et.append(dt)
         e2e_t = sum(et) / len(et)
-        e2e = {"value": flop / e2e_t / 1e9, "unit": UNIT, "seconds": e2e_t,
-               "h2d_bytes_per_step": int(s.info("value_bytes")) + int(s.info("ntask")) * 48,
-               "d2h_bytes_per_step": int(s.info("own_value_bytes"))}
+        e2e = {"value": flop / e2e_t / 1e9, "unit": UNIT, "seconds": e2e_t, "path": "pangulu_gstrf, host buffers in/out, resident plan",
+               "h2d_bytes_per_step": int(s.info("value_bytes")), "d2h_bytes_per_step": int(s.info("own_value_bytes"))}
         check_e2e = s.factor_check()
+        if a.abi_e2e:
+            # the same through the platform entry point PanguLU's scheduler calls: one <id>_hybrid_batched per wave with HOST
+            # task arrays (first-generation per-wave kernels, no plan)
+            s.set_mode(0)
+            s.reset_values(False)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            s.gstrf()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            e2e["hybrid_batched_per_wave"] = {"value": flop / dt / 1e9, "seconds": dt,
+                                              "h2d_bytes_per_step": int(s.info("value_bytes")) + int(s.info("ntask")) * 48}
     else:
         check_e2e = None
 
@@ -293,19 +314,22 @@ def run_ours(a):
     peaks, peak_kind = measured_peaks()
     names = ["getrf", "tstrf+gessm", "-", "ssssm_sparse", "ssssm_tile", "aux"]
     class_ms = class_ms + [0.0] * (7 - len(class_ms))
-    mega_ms = L.pangulu_sm100_stats_ms(6) / a.steps
-    mega_launches = L.pangulu_sm100_stats_launches(6) / a.steps
     launches += int(mega_launches)
     all_bytes = sum(s.info("bytes_" + k) for k in ("getrf", "tstrf", "gessm", "ssssm"))
     all_flop = s.info("flop")
     if mega_launches > 0:
-        ach = all_bytes / (mega_ms * 1e-3) / 1e9
-        roof = {"kernel": "mega_kernel (persistent executor: GETRF + TSTRF/GESSM + SSSSM sparse/tile tasks of this rank)", "bound": "hbm",
-                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                "peak_kind": f"hbm copy bandwidth, {peak_kind} (MEASURED_PEAKS.json)", "launches_per_step": mega_launches, "ms_per_step": mega_ms,
-                "algorithmic_bytes_per_launch": all_bytes,
-                "fp64_tflops": all_flop / (mega_ms * 1e-3) / 1e12,
-                "fp64_frac_of_nominal_40tf": all_flop / (mega_ms * 1e-3) / 1e12 / NOMINAL_FP64_TFLOPS}
+        # 96 % of the step's flops are SSSSM updates executed as compact dense products on the FP64 tensor pipe (DMMA.8x8x4):
+        # the kernel is bound by that pipe, not by HBM (its algorithmic byte rate is reported next to it)
+        tf = all_flop / (mega_ms * 1e-3) / 1e12
+        ach_gbs = all_bytes / (mega_ms * 1e-3) / 1e9
+        roof = {"kernel": "mega_kernel (persistent executor: GETRF + TSTRF/GESSM + SSSSM tasks of this rank in one launch)", "bound": "tensor",
+                "achieved": tf, "peak": MEASURED_DMMA_TFLOPS, "unit": "TFLOP/s", "frac": tf / MEASURED_DMMA_TFLOPS, "traffic": None,
+                "peak_kind": "FP64 tensor (DMMA.8x8x4) issue rate measured on this pool (scripts/micro/dmma_bench.cu, profiles/r01_dmma_microbench.txt); "
+                             "MEASURED_PEAKS.json has no FP64 entry; nominal 40 TFLOP/s",
+                "launches_per_step": mega_launches, "ms_per_step": mega_ms,
+                "algorithmic_flops_per_launch": all_flop, "algorithmic_bytes_per_launch": all_bytes,
+                "hbm": {"achieved_gbs": ach_gbs, "peak_gbs": peaks["hbm_gbs"], "frac": ach_gbs / peaks["hbm_gbs"], "peak_kind": f"{peak_kind} (MEASURED_PEAKS.json)"},
+                "fp64_frac_of_nominal_40tf": tf / NOMINAL_FP64_TFLOPS}
     else:
         dom = max(range(5), key=lambda c: class_ms[c])
         if dom in (3, 4):
@@ -323,6 +347,43 @@ def run_ours(a):
                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "peak_kind": f"hbm copy bandwidth, {peak_kind}",
                     "launches_per_step": class_launches[dom], "ms_per_step": class_ms[dom]}
         roof["class_ms"] = {names[c]: class_ms[c] for c in range(5) if c != 2}
+
+    # ---- device time per task class: one extra, traced step (per-task timestamps from %globaltimer; not part of the timing)
+    classes = None
+    if world == 1 and mega_launches > 0 and not a.no_classes:
+        L.pangulu_sm100_set_option(b"trace", 1)
+        L.pangulu_sm100_driver_rebuild_plan(s._h)
+        s.set_mode(1)
+        s.reset_values(True)
+        s.gstrf()
+        nt = int(L.pangulu_sm100_driver_trace(s._h, None, 0))
+        buf = np.zeros((nt, 4), dtype=np.uint64)
+        L.pangulu_sm100_driver_trace(s._h, buf.ctypes.data, nt)
+        kind = (buf[:, 0] & 0xff).astype(np.int64)
+        run = (buf[:, 3] - buf[:, 2]).astype(np.float64) * 1e-9
+        wait = (buf[:, 2] - buf[:, 1]).astype(np.float64) * 1e-9
+        span = float(buf[:, 3].max() - buf[:, 1].min()) * 1e-9
+        classes = {"span_s": span, "sm_count": 148, "capacity_cta_s": 148 * span}
+        for k, name in enumerate(TASK_KINDS):
+            m = kind == k
+            if m.any():
+                classes[name] = {"tasks": int(m.sum()), "busy_cta_s": float(run[m].sum()), "wait_cta_s": float(wait[m].sum())}
+        busy_ssssm = sum(classes[n]["busy_cta_s"] for n in ("ssssm_tile", "ssssm_sparse", "ssssm_compact") if n in classes)
+        busy_panel = sum(classes[n]["busy_cta_s"] for n in ("panel_sparse", "panel_compact") if n in classes)
+        busy_getrf = sum(classes[n]["busy_cta_s"] for n in ("getrf_smem", "getrf_dense", "getrf_global") if n in classes)
+        per_sm_tf = MEASURED_DMMA_TFLOPS / 148
+        per_sm_gbs = peaks["hbm_gbs"] / 148
+        # rate of a class WHILE one of its tasks occupies an SM, against one SM's share of the peak
+        classes["while_active"] = {
+            "ssssm": {"tflops_per_sm": s.info("flop_ssssm") / busy_ssssm / 1e12, "frac_of_dmma_peak": s.info("flop_ssssm") / busy_ssssm / 1e12 / per_sm_tf,
+                      "algorithmic_gbs_per_sm": s.info("bytes_ssssm") / busy_ssssm / 1e9, "frac_of_hbm_peak": s.info("bytes_ssssm") / busy_ssssm / 1e9 / per_sm_gbs},
+            "tstrf_gessm": {"tflops_per_sm": (s.info("flop_tstrf") + s.info("flop_gessm")) / busy_panel / 1e12,
+                            "frac_of_dmma_peak": (s.info("flop_tstrf") + s.info("flop_gessm")) / busy_panel / 1e12 / per_sm_tf,
+                            "algorithmic_gbs_per_sm": (s.info("bytes_tstrf") + s.info("bytes_gessm")) / busy_panel / 1e9,
+                            "frac_of_hbm_peak": (s.info("bytes_tstrf") + s.info("bytes_gessm")) / busy_panel / 1e9 / per_sm_gbs},
+            "getrf": {"algorithmic_gbs_per_sm": s.info("bytes_getrf") / busy_getrf / 1e9, "frac_of_hbm_peak": s.info("bytes_getrf") / busy_getrf / 1e9 / per_sm_gbs},
+        }
+        L.pangulu_sm100_set_option(b"trace", 0)
 
     cpu = None
     if not a.no_cpu_baseline and rank == 0 and world == 1:
@@ -352,7 +413,7 @@ def run_ours(a):
                        "waves": int(s.info("nwave")), "tasks": int(s.info("ntask")),
                        "l2": "inputs (factor values %.1f GB) exceed the 126 MB L2; values are rewritten between steps" % (s.info("value_bytes") / 1e9),
                        "init_seconds": t_init},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "classes": classes, "cpu_baseline": cpu,
             "parity": {"factor_check_resident": check, "factor_check_e2e": check_e2e}}
     s.finalize()
     if rank == 0:

@@ -51,7 +51,8 @@ void pangulu_finalize(void **pangulu_handle);
  * rank/size from MPI_COMM_WORLD):
  *   "rank", "nproc"   position in the p x q rank grid (one rank per GPU)
  *   "ordering"        0 natural (input already permuted), 1 METIS_NodeND, -1 (default) METIS when built in
- *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan
+ *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan,
+ *                     2 host buffers + resident plan (upload values, run the plan, download factors)
  *   "schedule"        wave of an SSSSM update: 0 lazy (the wave that finalises its destination), 1 eager (first wave
  *                     after both operands are final), 2 (default) windowed: max(eager, destination's wave - "lookahead")
  *   "lookahead"       window of policy 2 in waves (default 6)
@@ -71,7 +72,7 @@ pangulu_storage_slot_t *pangulu_sm100_driver_slot(void *handle, long long i);
 const void *pangulu_sm100_driver_perm(void *handle, int which);
 /* the static schedule: tasks sorted by wave, wave_ptr has nwave+1 entries */
 const pangulu_task_t *pangulu_sm100_driver_tasks(void *handle, const pangulu_uint64_t **wave_ptr);
-/* switch an initialised handle between the two gstrf modes (0 reference-facing, 1 resident plan) */
+/* switch an initialised handle between the gstrf modes (0 reference-facing, 1 resident plan, 2 host buffers + plan) */
 void pangulu_sm100_driver_set_mode(void *handle, int mode);
 /* put the values of A back into the host block buffers (and the device copy) so gstrf can run again */
 void pangulu_sm100_driver_reset_values(void *handle, int also_device);
@@ -89,6 +90,8 @@ long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *h
 void pangulu_sm100_driver_commit(void *handle);
 void pangulu_sm100_driver_gstrf_reset(void *handle);
 void pangulu_sm100_driver_gstrf_launch(void *handle);
+/* drop and rebuild the device-resident plan with the platform options in force now (e.g. "trace") */
+void pangulu_sm100_driver_rebuild_plan(void *handle);
 /* task trace of the last resident gstrf (see pangulu_sm100_plan_trace) */
 long long pangulu_sm100_driver_trace(void *handle, unsigned long long *out, long long cap);
 /* device -> host copy of the owned factors (resident mode) */

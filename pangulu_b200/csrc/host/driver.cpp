@@ -12,6 +12,7 @@
 //      back to the host buffers -- all inside the call (what bench.py reports as "e2e");
 //   1  resident: the schedule was translated once into a device-resident plan; gstrf only enqueues the
 //      plan on values already in HBM and synchronises (bench.py's "value").
+//   2  host buffers + resident plan: upload the value region, run the plan, download the factors (bench.py's "e2e").
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -218,6 +219,17 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
         pangulu_sm100_plan_execute(h->plan);
         PSM(synchronize)();
     }
+    else if (h->mode == 2)
+    {
+        // host buffers in, host buffers out, resident plan in between: what a PanguLU user sees from pangulu_gstrf
+        if (!h->plan)
+            h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
+                                                h->sched.tasks.data());
+        PSM(memcpy)(B.d_buf, B.h_buf, B.value_bytes, 0);
+        pangulu_sm100_plan_execute(h->plan);
+        PSM(synchronize)();
+        PSM(memcpy)(B.h_buf, B.d_buf, B.own_value_bytes, 1);
+    }
     else
     {
         const long long eager = pangulu_sm100_get_option("eager_download");
@@ -352,6 +364,16 @@ const pangulu_task_t* pangulu_sm100_driver_tasks(void* handle, const pangulu_uin
 }
 
 void pangulu_sm100_driver_set_mode(void* handle, int mode) { ((Handle*)handle)->mode = mode; }
+
+// drop the device-resident plan and build it again with the platform options in force now (e.g. "trace")
+void pangulu_sm100_driver_rebuild_plan(void* handle)
+{
+    Handle* h = (Handle*)handle;
+    if (h->B.host_only) return;
+    if (h->plan) pangulu_sm100_plan_destroy(h->plan);
+    h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
+                                        h->sched.tasks.data());
+}
 
 void pangulu_sm100_driver_reset_values(void* handle, int also_device)
 {
