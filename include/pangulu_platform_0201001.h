@@ -114,6 +114,11 @@ long long pangulu_sm100_get_option(const char *key);
 
 /* release memory obtained from <id>_malloc_pinned (the reference interface has no such call and leaks it) */
 void pangulu_sm100_free_pinned(void *host_ptr);
+/* Independent groups of a diagonal block (index ranges bounds[g] .. bounds[g+1], g < ngroups <= 4, over which the block
+ * is block diagonal).  Once registered for the block's LOWER-half slot, a GETRF task factors only the group named in
+ * bits 32.. of its compare_flag, updates of the block count towards the groups they touch and TSTRF/GESSM wait only
+ * for the groups they read.  ngroups <= 1 removes the entry; lower_half == NULL clears the registry. */
+void pangulu_sm100_set_diag_groups(const pangulu_storage_slot_t *lower_half, int ngroups, const unsigned short *bounds);
 
 /* Copy the values of n blocks device -> host (slot->d_value -> slot->value) in one pass. */
 void pangulu_sm100_download_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t **slots);

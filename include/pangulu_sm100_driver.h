@@ -51,6 +51,8 @@ void pangulu_finalize(void **pangulu_handle);
  * rank/size from MPI_COMM_WORLD):
  *   "rank", "nproc"   position in the p x q rank grid (one rank per GPU)
  *   "ordering"        0 natural (input already permuted), 1 METIS_NodeND, -1 (default) METIS when built in
+ *   "split_diag"      1 (default): independent groups of diagonal blocks get their own GETRF task and dependency
+ *                     counters (single rank), 0: one GETRF per diagonal block
  *   "mode"            0 reference-facing gstrf (host buffers, per-wave hybrid_batched), 1 resident plan,
  *                     2 host buffers + resident plan (upload values, run the plan, download factors)
  *   "schedule"        wave of an SSSSM update: 0 lazy (the wave that finalises its destination), 1 eager (first wave

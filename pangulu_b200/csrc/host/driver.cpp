@@ -37,6 +37,7 @@ struct DriverConfig
     long long host_only = 0;
     long long schedule = 2;
     long long lookahead = 6;
+    long long split_diag = 1;  // schedule independent groups of diagonal blocks separately (single rank)
 };
 DriverConfig g_cfg;
 void (*g_barrier)(void) = nullptr;  // host barrier across ranks (multi-GPU), installed by the launcher
@@ -75,6 +76,7 @@ int pangulu_sm100_driver_config(const char* key, long long value)
     else if (k == "host_only") g_cfg.host_only = value;
     else if (k == "schedule") g_cfg.schedule = value;
     else if (k == "lookahead") g_cfg.lookahead = value;
+    else if (k == "split_diag") g_cfg.split_diag = value;
     else return -1;
     return 0;
 }
@@ -160,7 +162,13 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     t0 = wall_seconds();
     h->sched.policy = (int)g_cfg.schedule;
     h->sched.lookahead = (int)g_cfg.lookahead;
+    h->sched.split_diag = (int)g_cfg.split_diag;
     build_schedule(h->B, h->sched);
+    if (!h->B.host_only)
+        for (eidx k = 0; k < h->B.block_length; ++k)
+            if (h->sched.group_count[k] > 1 && h->B.slot_of_diag[k] >= 0)
+                pangulu_sm100_set_diag_groups(&h->B.slots[h->B.slot_of_diag[k]], h->sched.group_count[k],
+                                              &h->sched.group_bounds[(size_t)k * (DIAG_MAX_GROUPS + 1)]);
     h->times["schedule"] = wall_seconds() - t0;
     t0 = wall_seconds();
     work_model(h->B, h->sched, h->work);
@@ -287,6 +295,10 @@ void pangulu_finalize(void** pangulu_handle)
     Handle* h = (Handle*)*pangulu_handle;
     if (!h) return;
     if (h->plan) pangulu_sm100_plan_destroy(h->plan);
+    if (!h->B.host_only)
+        for (eidx k = 0; k < h->B.block_length; ++k)
+            if (h->sched.group_count.size() > k && h->sched.group_count[k] > 1 && h->B.slot_of_diag[k] >= 0)
+                pangulu_sm100_set_diag_groups(&h->B.slots[h->B.slot_of_diag[k]], 0, nullptr);
     free_blocks(h->B);
     delete h;
     *pangulu_handle = NULL;
@@ -308,6 +320,12 @@ double pangulu_sm100_driver_info(void* handle, const char* key)
     if (k == "num_own_diag") return (double)h->B.n_own_diag;
     if (k == "num_blocks_global") return (double)h->B.bcol_ptr[h->B.block_length] + h->B.block_length;
     if (k == "nwave") return (double)(h->sched.wave_ptr.size() - 1);
+    if (k == "n_split_diag")
+    {
+        double c = 0;
+        for (uint8_t g : h->sched.group_count) c += g > 1;
+        return c;
+    }
     if (k == "ntask") return (double)h->sched.tasks.size();
     if (k == "n_getrf") return (double)h->sched.n_getrf;
     if (k == "n_tstrf") return (double)h->sched.n_tstrf;

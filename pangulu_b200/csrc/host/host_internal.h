@@ -115,12 +115,19 @@ void build_blocks(const Csc& A, const Symbolic& S, int nb, int rank, int nproc, 
 void free_blocks(BlockStore& B);
 
 // ---- static schedule ----
+#define DIAG_MAX_GROUPS 4
 struct Schedule
 {
     std::vector<pangulu_task_t> tasks;  // sorted by wave
     std::vector<uint64_t> wave_ptr;     // nwave + 1
     std::vector<int32_t> depth_offdiag; // per global off-diagonal block
-    std::vector<int32_t> depth_diag;    // per block row
+    std::vector<int32_t> depth_diag;    // per block row and group: [k * DIAG_MAX_GROUPS + g]
+    // independent parts of the diagonal blocks (schedule.cpp: diag_groups)
+    int split_diag = 1;
+    std::vector<uint16_t> group_bounds; // [k * (DIAG_MAX_GROUPS+1) + g] .. [+ g + 1): index range of group g of diagonal block k
+    std::vector<uint8_t> group_count;   // per block row
+    std::vector<uint8_t> colgroups;     // per global off-diagonal block (I,J): groups of diagonal block J its columns touch
+    std::vector<uint8_t> rowgroups;     //                                       groups of diagonal block I its rows touch
     uint64_t n_getrf = 0, n_tstrf = 0, n_gessm = 0, n_ssssm = 0;
     int policy = 2;                     // 0 lazy (updates in the destination's wave), 1 eager (as soon as operands are final), 2 windowed
     int lookahead = 6;                  // policy 2: waves before the destination's finalisation at which slack updates run

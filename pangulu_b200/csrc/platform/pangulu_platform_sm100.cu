@@ -92,6 +92,15 @@ struct Ctx
 };
 Ctx g;
 
+// independent groups of diagonal blocks (set by the host driver; keyed by the LOWER-half slot): bounds[0..ng]
+struct DiagGroupInfo { int ng; unsigned short bounds[5]; };
+std::unordered_map<const pangulu_storage_slot_t*, DiagGroupInfo> g_diag_groups;
+inline const DiagGroupInfo* groups_of(const pangulu_storage_slot_t* lower)
+{
+    auto it = g_diag_groups.find(lower);
+    return it == g_diag_groups.end() ? nullptr : &it->second;
+}
+
 void ensure_ctx()
 {
     if (g.stream) return;
@@ -359,6 +368,21 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
             });
             std::vector<SsssmDest<T>> by_cls[3];
             std::vector<pangulu_storage_slot_t*> cslot;  // destination slots of by_cls[2]
+            const DiagGroupInfo* cur_groups = nullptr;    // groups of the current (diagonal) destination, if it has several
+            // groups of a diagonal destination that an update touches = groups in which its left operand has rows (flags bits 8..11)
+            auto touched_groups = [&](const pangulu_storage_slot_t* a, const DiagGroupInfo* gi) -> u32 {
+                if (!gi || gi->ng <= 1) return 1u;
+                u32 m = 0;
+                const u32 nnz = a->columnpointer[nb];
+                for (u32 q = 0; q < nnz; ++q)
+                {
+                    const u16 r = a->rowindex[q];
+                    int gr = 0;
+                    while (gr + 1 < gi->ng && r >= gi->bounds[gr + 1]) ++gr;
+                    m |= 1u << gr;
+                }
+                return m;
+            };
             const void* cur = nullptr;
             int cur_cls = -1;
             for (size_t k : order)
@@ -379,17 +403,20 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                         D.c.rptr = nullptr; D.c.ridx = nullptr; D.c.rmap = nullptr;
                         D.u = blk_upper_diag(up);
                         D.nnz_c = slot_nnz(nb, lo) + slot_nnz(nb, up);
+                        cur_groups = groups_of(lo);
                     }
                     else
                     {
                         D.c = blk_csc(d);
                         D.nnz_c = slot_nnz(nb, d);
+                        cur_groups = nullptr;
                     }
                     D.pair_begin = (u32)(cur_cls == 2 ? P.cpairs.size() : P.pairs.size());
                     D.pair_end = D.pair_begin;
                     by_cls[cur_cls].push_back(D);
                     if (cur_cls == 2) cslot.push_back(d);
                 }
+                by_cls[cur_cls].back().flags |= touched_groups(t.op1, cur_groups) << 8;
                 if (cur_cls == 2)
                 {
                     CPair cp;
@@ -505,8 +532,8 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
         {
             size_t j = i;
             // diagonal blocks that fit in shared memory (values + pattern of both halves) take the staged kernel
-            std::vector<GetrfTask<T>> fit, big;
-            std::vector<const pangulu_storage_slot_t*> fit_slot, big_slot;
+            std::vector<GetrfTask<T>> fit, big, glob;
+            std::vector<const pangulu_storage_slot_t*> fit_slot, big_slot, glob_slot;
             size_t fit_smem = 0;
             Step dl; dl.kind = -1; dl.off = P.downloads.size(); dl.count = 0;
             while (j < t1 && tasks[j].kernel_id == PANGULU_TASK_GETRF)
@@ -516,11 +543,23 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 GetrfTask<T> G;
                 G.lower = blk_csc(lo);
                 G.upper = blk_upper_diag(up);
-                const size_t nl = slot_nnz(nb, lo), nu = slot_nnz(nb, up);
+                G.c0 = 0; G.c1 = nb; G.grp = 0; G.pad = 0;
+                const DiagGroupInfo* gi = groups_of(lo);
+                if (gi && gi->ng > 1)
+                {
+                    G.grp = (int)(tasks[j].compare_flag >> 32);
+                    if (G.grp < 0 || G.grp >= gi->ng) fatal(__FILE__, __LINE__, "GETRF task names a group the diagonal block does not have", nullptr);
+                    G.c0 = gi->bounds[G.grp];
+                    G.c1 = gi->bounds[G.grp + 1];
+                }
+                const bool grouped = G.c0 != 0 || G.c1 != nb;
+                auto cb = [&](const pangulu_storage_slot_t* sl2, int c) { return c == 0 ? 0u : sl2->columnpointer[c]; };
+                const size_t nl = lo->columnpointer[G.c1] - cb(lo, G.c0), nu = up->columnpointer[G.c1] - cb(up, G.c0);
                 const size_t need = getrf_smem_bytes(nb, nl, nu);
                 // getrf_mode: 0 auto, 1 never stage in shared memory, 2 never promote to dense, 3 always dense (nb <= 256)
-                const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256;
+                const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256 && !grouped;
                 if (!want_dense && need + 512 <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); fit_slot.push_back(lo); }
+                else if (grouped) { glob.push_back(G); glob_slot.push_back(lo); }   // a group never takes the dense whole-block kernel
                 else { big.push_back(G); big_slot.push_back(lo); }
                 if (eager_download)
                 {
@@ -545,6 +584,13 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 P.getrf_slot.insert(P.getrf_slot.end(), big_slot.begin(), big_slot.end());
                 P.steps.push_back(st);
             }
+            if (!glob.empty())
+            {
+                Step st; st.kind = (int)K_GETRF; st.off = P.getrf.size(); st.count = glob.size(); st.smem = 0;
+                P.getrf.insert(P.getrf.end(), glob.begin(), glob.end());
+                P.getrf_slot.insert(P.getrf_slot.end(), glob_slot.begin(), glob_slot.end());
+                P.steps.push_back(st);
+            }
             if (dl.count) P.steps.push_back(dl);
             i = j;
         }
@@ -563,6 +609,28 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 Q.kind = t.kernel_id;
                 Q.dense = -1;
                 Q.b = blk_csc(t.opdst);
+                {
+                    // TSTRF: groups in which the block has columns; GESSM: groups in which it has rows
+                    u32 m = 1u;
+                    const DiagGroupInfo* gi = groups_of(lo);
+                    if (gi && gi->ng > 1)
+                    {
+                        m = 0;
+                        auto grp_of = [&](int x) { int gr = 0; while (gr + 1 < gi->ng && x >= gi->bounds[gr + 1]) ++gr; return gr; };
+                        if (t.kernel_id == PANGULU_TASK_TSTRF)
+                        {
+                            for (int c = 0; c < nb; ++c)
+                                if (t.opdst->columnpointer[c + 1] > (c ? t.opdst->columnpointer[c] : 0u)) m |= 1u << grp_of(c);
+                        }
+                        else
+                        {
+                            const u32 nnz = t.opdst->columnpointer[nb];
+                            for (u32 q = 0; q < nnz; ++q) m |= 1u << grp_of(t.opdst->rowindex[q]);
+                        }
+                        if (m == 0) m = 1u;
+                    }
+                    Q.kind |= (int)(m << 8);
+                }
                 if (t.kernel_id == PANGULU_TASK_TSTRF)
                 {
                     if (!Q.b.rptr) fatal(__FILE__, __LINE__, "TSTRF destination has no CSR mirror (must be a strictly-lower block)", nullptr);
@@ -922,8 +990,11 @@ void build_mega(pangulu_sm100_plan* pl)
         return id;
     };
     std::vector<MegaTask> tasks;
-    std::vector<int> dest_id(P.dests.size(), 0), remaining, pending;
+    std::vector<int> remaining, pending;
+    std::vector<int4> dest_id(P.dests.size(), make_int4(0, -1, -1, -1)), panel_dep(P.panel.size(), make_int4(0, -1, -1, -1));
     std::vector<int2> pair_dep(P.pairs.size()), getrf_id(P.getrf.size()), panel_id(P.panel.size()), cpair_dep(P.cpairs.size());
+    // sync id of group gr of a diagonal half: the value pointer plus gr (value arrays are 16-byte aligned, gr < 4)
+    auto gkey = [](const void* val, int gr) -> const void* { return (const char*)val + gr; };
     std::vector<char> produced;
     auto touch = [&](int id) {
         if ((size_t)id >= remaining.size()) { remaining.resize(id + 1, 0); produced.resize(id + 1, 0); pending.resize(id + 1, 0); }
@@ -951,20 +1022,26 @@ void build_mega(pangulu_sm100_plan* pl)
         case K_SSSSM_CTILE:
             for (size_t d = st.off; d < st.off + st.count; ++d)
             {
-                const int id = id_of(P.dests[d].c.val);
-                touch(id);
-                dest_id[d] = id;
+                // a diagonal destination counts towards every group its updates touch (flags bits 8..11), any other towards itself
+                int ids4[4] = {-1, -1, -1, -1};
+                int nid4 = 0;
+                const u32 gm = P.dests[d].u.val ? ((P.dests[d].flags >> 8) & 0xfu) : 1u;
+                for (int gr = 0; gr < 4; ++gr)
+                    if ((gm >> gr) & 1u) { ids4[nid4] = id_of(gkey(P.dests[d].c.val, gr)); touch(ids4[nid4]); ++nid4; }
+                if (nid4 == 0) { ids4[0] = id_of(P.dests[d].c.val); touch(ids4[0]); nid4 = 1; }
+                dest_id[d] = make_int4(ids4[0], ids4[1], ids4[2], ids4[3]);
+                auto count = [&](int n) { for (int q = 0; q < nid4; ++q) remaining[ids4[q]] += n; };
                 if (st.kind == K_SSSSM_CTILE)
                     ;  // tile tasks below
                 else if (st.kind == K_SSSSM_TILE)
                 {
                     for (int t = 0; t < tiles; ++t) tasks.push_back({MEGA_TILE, (int)d, t, (int)(P.dests[d].pair_end - P.dests[d].pair_begin)});
-                    remaining[id] += tiles;
+                    count(tiles);
                 }
                 else
                 {
                     for (int t = 0; t < sgroups; ++t) tasks.push_back({MEGA_SPARSE, (int)d, t * sgroup, sgroup});
-                    remaining[id] += sgroups;
+                    count(sgroups);
                 }
             }
             if (st.kind == K_SSSSM_CTILE)
@@ -972,7 +1049,11 @@ void build_mega(pangulu_sm100_plan* pl)
                 {
                     const CTileTask& ct = P.ctasks[c];
                     tasks.push_back({MEGA_CTILE, ct.dest, ct.clo | (ct.chi << 16), (int)(P.dests[ct.dest].pair_end - P.dests[ct.dest].pair_begin)});
-                    remaining[dest_id[ct.dest]] += 1;
+                    const int4 di = dest_id[ct.dest];
+                    remaining[di.x] += 1;
+                    if (di.y >= 0) remaining[di.y] += 1;
+                    if (di.z >= 0) remaining[di.z] += 1;
+                    if (di.w >= 0) remaining[di.w] += 1;
                 }
             break;
         case K_GETRF:
@@ -980,7 +1061,7 @@ void build_mega(pangulu_sm100_plan* pl)
         case K_GETRF_DENSE:
             for (size_t gi = st.off; gi < st.off + st.count; ++gi)
             {
-                const int il = id_of(P.getrf[gi].lower.val), iu = id_of(P.getrf[gi].upper.val);
+                const int il = id_of(gkey(P.getrf[gi].lower.val, P.getrf[gi].grp)), iu = id_of(gkey(P.getrf[gi].upper.val, P.getrf[gi].grp));
                 touch(il);
                 touch(iu);
                 getrf_id[gi] = make_int2(il, iu);
@@ -992,10 +1073,15 @@ void build_mega(pangulu_sm100_plan* pl)
         case K_CPANEL:
             for (size_t ti = st.off; ti < st.off + st.count; ++ti)
             {
-                const int ib = id_of(P.panel[ti].b.val), idg = id_of(P.panel[ti].diag.val);
+                const int ib = id_of(P.panel[ti].b.val);
                 touch(ib);
-                touch(idg);
-                panel_id[ti] = make_int2(ib, idg);
+                int dp[4] = {-1, -1, -1, -1}, ndp = 0;
+                const u32 gm = ((u32)P.panel[ti].kind >> 8) & 0xfu;
+                for (int gr = 0; gr < 4; ++gr)
+                    if ((gm >> gr) & 1u) { dp[ndp] = id_of(gkey(P.panel[ti].diag.val, gr)); touch(dp[ndp]); ++ndp; }
+                if (ndp == 0) { dp[0] = id_of(P.panel[ti].diag.val); touch(dp[0]); }
+                panel_dep[ti] = make_int4(dp[0], dp[1], dp[2], dp[3]);
+                panel_id[ti] = make_int2(ib, dp[0]);
                 produced[ib] = 1;
                 if (st.kind == K_TSTRF)
                     for (int r0 = 0; r0 < nb; r0 += 64) { tasks.push_back({MEGA_PANEL, (int)ti, r0, 0}); pending[ib]++; }
@@ -1015,11 +1101,11 @@ void build_mega(pangulu_sm100_plan* pl)
     for (size_t i = 0; i < nid; ++i) done_init[i] = produced[i] ? 0 : 1;  // blocks no task of this plan produces are final already
 
     const int nbp = (nb + 31) & ~31;
-    const size_t sz_tasks = vbytes(tasks), sz_pd = vbytes(pair_dep), sz_di = vbytes(dest_id), sz_gi = vbytes(getrf_id), sz_pi = vbytes(panel_id), sz_cd = vbytes(cpair_dep);
+    const size_t sz_tasks = vbytes(tasks), sz_pd = vbytes(pair_dep), sz_di = vbytes(dest_id), sz_gi = vbytes(getrf_id), sz_pi = vbytes(panel_id), sz_cd = vbytes(cpair_dep), sz_pp = vbytes(panel_dep);
     const size_t sz_ids = (nid * sizeof(int) + 255) & ~(size_t)255;
     const size_t sz_scratch = ((size_t)g.sm_count * nbp * nbp * sizeof(T) + 255) & ~(size_t)255;
     const size_t sz_trace = g.opt.trace ? ((tasks.size() * 3 * sizeof(unsigned long long) + 255) & ~(size_t)255) : 0;
-    const size_t total = sz_tasks + sz_pd + sz_di + sz_gi + sz_pi + sz_cd + 6 * sz_ids + 256 + sz_scratch + sz_trace;
+    const size_t total = sz_tasks + sz_pd + sz_di + sz_gi + sz_pi + sz_cd + sz_pp + 6 * sz_ids + 256 + sz_scratch + sz_trace;
     char* d = nullptr;
     CK(cudaMalloc((void**)&d, total));
     pl->mega_buf = d;
@@ -1035,10 +1121,11 @@ void build_mega(pangulu_sm100_plan* pl)
     mp.ntask = (int)tasks.size();
     mp.tasks = (const MegaTask*)put(tasks.data(), tasks.size() * sizeof(MegaTask), sz_tasks);
     mp.pair_dep = (const int2*)put(pair_dep.data(), pair_dep.size() * sizeof(int2), sz_pd);
-    mp.dest_id = (const int*)put(dest_id.data(), dest_id.size() * sizeof(int), sz_di);
+    mp.dest_id = (const int4*)put(dest_id.data(), dest_id.size() * sizeof(int4), sz_di);
     mp.getrf_id = (const int2*)put(getrf_id.data(), getrf_id.size() * sizeof(int2), sz_gi);
     mp.panel_id = (const int2*)put(panel_id.data(), panel_id.size() * sizeof(int2), sz_pi);
     mp.cpair_dep = (const int2*)put(cpair_dep.data(), cpair_dep.size() * sizeof(int2), sz_cd);
+    mp.panel_dep = (const int4*)put(panel_dep.data(), panel_dep.size() * sizeof(int4), sz_pp);
     mp.cpairs = pl->D.cpairs;
     mp.ops = pl->D.ops;
     mp.cptasks = pl->D.cptasks;
@@ -1269,6 +1356,17 @@ long long pangulu_sm100_get_option(const char* key)
     return p ? *p : -1;
 }
 
+void pangulu_sm100_set_diag_groups(const pangulu_storage_slot_t* lower_half, int ngroups, const unsigned short* bounds)
+{
+    if (!lower_half) { g_diag_groups.clear(); return; }
+    if (ngroups <= 1) { g_diag_groups.erase(lower_half); return; }
+    if (ngroups > 4) fatal(__FILE__, __LINE__, "at most 4 groups per diagonal block", nullptr);
+    DiagGroupInfo gi;
+    gi.ng = ngroups;
+    for (int i = 0; i <= ngroups; ++i) gi.bounds[i] = bounds[i];
+    g_diag_groups[lower_half] = gi;
+}
+
 void pangulu_sm100_free_pinned(void* host_ptr) { if (host_ptr) CK(cudaFreeHost(host_ptr)); }
 
 void pangulu_sm100_download_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t** slots)
@@ -1361,7 +1459,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             compact[i] = 1;
             diag_of[i] = it->second;
             DiagNeed& dn = need[it->second];
-            if (P.panel[i].kind == PANGULU_TASK_GESSM) dn.lt = true; else dn.u = true;
+            if ((P.panel[i].kind & 0xff) == PANGULU_TASK_GESSM) dn.lt = true; else dn.u = true;
         }
         const size_t tri = (size_t)(nb / 16) * nb * PSM_CT_BLD;  // values per triangular copy
         size_t total = 0;
@@ -1369,6 +1467,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
         {
             auto it = need.find(P.getrf_slot[gi]);
             if (it == need.end()) continue;
+            if (it->second.index >= 0) { P.getrf_dd[gi] = it->second.index; continue; }  // another group of the same block
             it->second.index = (int)dds.size();
             P.getrf_dd[gi] = it->second.index;
             DiagDense<T> dd;

@@ -611,12 +611,13 @@ template <class T>
 __device__ __forceinline__ void diag_densify(int nb, const GetrfTask<T>& G, const DiagDense<T>& DD)
 {
     const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP, nw = blockDim.x / PSM_WARP;
+    (void)nb;
     if (DD.u)
-        for (int r = warp; r < nb; r += nw)   // row r of U (CSR, diagonal first)
+        for (int r = G.c0 + warp; r < G.c1; r += nw)   // row r of U (CSR, diagonal first); only the task's group
             for (u32 e = col_begin(G.upper.ptr, r) + lane; e < G.upper.ptr[r + 1]; e += PSM_WARP)
                 DD.u[((size_t)(r / 16) * nb + G.upper.idx[e]) * PSM_CT_BLD + (r % 16)] = G.upper.val[e];
     if (DD.lt)
-        for (int k = warp; k < nb; k += nw)   // column k of L (CSC): L(c,k) = L^T(k,c)
+        for (int k = G.c0 + warp; k < G.c1; k += nw)   // column k of L (CSC): L(c,k) = L^T(k,c)
             for (u32 e = col_begin(G.lower.ptr, k) + lane; e < G.lower.ptr[k + 1]; e += PSM_WARP)
                 DD.lt[((size_t)(k / 16) * nb + G.lower.idx[e]) * PSM_CT_BLD + (k % 16)] = G.lower.val[e];
 }
@@ -632,7 +633,7 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     unsigned char* tb0 = smem_raw + Lay::x_bytes;                         // 2 x [16 K][16 cols][20]
     __shared__ __align__(8) unsigned long long cbars[2];
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
-    const bool gessm = Q.kind == PANGULU_TASK_GESSM;
+    const bool gessm = (Q.kind & 0xff) == PANGULU_TASK_GESSM;
     const T* Tm = gessm ? DD.lt : DD.u;
     const u32* tmask = gessm ? DD.ltmask : DD.umask;
     const u32 kmask = Dn.kmask;

@@ -170,7 +170,7 @@ __device__ __forceinline__ void panel_solve_line(int nb, const PanelTask<T>& P, 
 {
     const int lane = threadIdx.x % PSM_WARP;
     const Blk<T> B = P.b, Dg = P.diag;
-    const bool gessm = P.kind == PANGULU_TASK_GESSM;
+    const bool gessm = (P.kind & 0xff) == PANGULU_TASK_GESSM;
     // GESSM: column rc of B (CSC), L = strict-lower CSC of the diagonal block (unit diagonal)
     // TSTRF: row rc of B through its CSR mirror, U = upper CSR of the diagonal block (diagonal first)
     const u32* bptr = gessm ? B.ptr : B.rptr;
@@ -272,21 +272,22 @@ panel_solve_kernel(int nb, const PanelTask<T>* __restrict__ tasks, int groups_pe
 // work) first and then already prepares that level (divides L(:,ln) by the clamped pivot, scatters it and U(ln,:)
 // into the other pair of dense vectors).  Every entry still sees the same operations in the same order.
 template <class T, int THREADS>
-__device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, const u16* lidx, T* uval, const u32* uptr, const u16* uidx, T* buf)
+__device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, const u16* lidx, T* uval, const u32* uptr, const u16* uidx, T* buf, int c0 = 0, int c1 = -1)
 {
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
     constexpr int NW = THREADS / PSM_WARP;
+    if (c1 < 0) c1 = nb;   // levels [c0, c1): one independent group of the block (rows / columns outside it are not touched)
     // next level >= from that has something to do: a non-empty U row (rows beyond n are padding,
     // pangulu_platform_0100000.c:74-77) and more than the pivot alone
     auto next_level = [&](int from) {
-        for (int l = from; l < nb; ++l)
+        for (int l = from; l < c1; ++l)
         {
             const u32 u0 = col_begin(uptr, l), u1 = uptr[l + 1];
             if (u0 == u1) continue;
             if (col_begin(lptr, l) == lptr[l + 1] && u1 - u0 == 1) continue;
             return l;
         }
-        return nb;
+        return c1;
     };
     // warp 0: scale L(:,l), scatter it and U(l,:) into the vectors of parity `par`, after clearing what level `old`
     // left there
@@ -330,11 +331,11 @@ __device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, con
         }
     };
 
-    int level = next_level(0), prev_level = -1, par = 0;
-    if (level >= nb) return;
+    int level = next_level(c0), prev_level = -1, par = 0;
+    if (level >= c1) return;
     if (warp == 0) prepare(level, 0, -1);
     __syncthreads();
-    while (level < nb)
+    while (level < c1)
     {
         const int ln = next_level(level + 1);
         const T* lcol = buf + (size_t)(par * 2) * nb;
@@ -345,7 +346,7 @@ __device__ __forceinline__ void getrf_body(int nb, T* lval, const u32* lptr, con
         if (warp == 0)
         {
             // critical path: row ln and column ln first (if level `level` touches them), then prepare level ln
-            if (ln < nb)
+            if (ln < c1)
             {
                 bool hit = false;
                 for (u32 e = l0 + lane; e < l1 && !hit; e += PSM_WARP) hit = lidx[e] == ln;
@@ -390,7 +391,7 @@ getrf_sparse_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
     const GetrfTask<T> G = tasks[blockIdx.x];
     for (int i = threadIdx.x; i < 4 * nb; i += THREADS) buf[i] = zero<T>();
     __syncthreads();
-    getrf_body<T, THREADS>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf);
+    getrf_body<T, THREADS>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf, G.c0, G.c1);
 }
 
 // variant 2: the whole block (values, pointers, indices of both halves) is staged in shared memory, so a
@@ -402,7 +403,11 @@ template <class T, int THREADS>
 __device__ __forceinline__ void getrf_smem_cta(unsigned char* smem_raw, int nb, const GetrfTask<T>& G)
 {
     const int tid = threadIdx.x;
-    const u32 nl = G.lower.ptr[nb], nu = G.upper.ptr[nb];
+    // only the entries of the group [c0, c1) are staged (columns c0..c1-1 of the lower half, rows c0..c1-1 of the upper
+    // half: the block is block diagonal over its groups); the shared-memory arrays are addressed with GLOBAL entry numbers
+    const int c0 = G.c0, c1 = G.c1;
+    const u32 lb = col_begin(G.lower.ptr, c0), le = G.lower.ptr[c1], ub = col_begin(G.upper.ptr, c0), ue = G.upper.ptr[c1];
+    const u32 nl = le - lb, nu = ue - ub;
     T* buf = reinterpret_cast<T*>(smem_raw);
     T* lval = buf + 4 * nb;
     T* uval = lval + nl;
@@ -411,14 +416,14 @@ __device__ __forceinline__ void getrf_smem_cta(unsigned char* smem_raw, int nb, 
     u16* lidx = reinterpret_cast<u16*>(uptr + (nb + 1));
     u16* uidx = lidx + nl;
     for (int i = tid; i < 4 * nb; i += THREADS) buf[i] = zero<T>();
-    for (u32 i = tid; i < nl; i += THREADS) { lval[i] = G.lower.val[i]; lidx[i] = G.lower.idx[i]; }
-    for (u32 i = tid; i < nu; i += THREADS) { uval[i] = G.upper.val[i]; uidx[i] = G.upper.idx[i]; }
+    for (u32 i = tid; i < nl; i += THREADS) { lval[i] = G.lower.val[lb + i]; lidx[i] = G.lower.idx[lb + i]; }
+    for (u32 i = tid; i < nu; i += THREADS) { uval[i] = G.upper.val[ub + i]; uidx[i] = G.upper.idx[ub + i]; }
     for (int i = tid; i <= nb; i += THREADS) { lptr[i] = i == 0 ? 0u : G.lower.ptr[i]; uptr[i] = i == 0 ? 0u : G.upper.ptr[i]; }
     __syncthreads();
-    getrf_body<T, THREADS>(nb, lval, lptr, lidx, uval, uptr, uidx, buf);
+    getrf_body<T, THREADS>(nb, lval - lb, lptr, lidx - lb, uval - ub, uptr, uidx - ub, buf, c0, c1);
     __syncthreads();
-    for (u32 i = tid; i < nl; i += THREADS) G.lower.val[i] = lval[i];
-    for (u32 i = tid; i < nu; i += THREADS) G.upper.val[i] = uval[i];
+    for (u32 i = tid; i < nl; i += THREADS) G.lower.val[lb + i] = lval[i];
+    for (u32 i = tid; i < nu; i += THREADS) G.upper.val[ub + i] = uval[i];
 }
 
 template <class T, int THREADS>
@@ -1159,11 +1164,12 @@ struct MegaParams
     const CPanelTask* cptasks;  // slices of the compact panel solves
     const DiagDense<T>* dds;    // dense triangular copies of diagonal blocks
     const int* getrf_dd;        // per GETRF task: index into dds or -1
-    const int* dest_id;     // per destination descriptor: sync id of the destination
+    const int4* dest_id;    // per destination descriptor: sync ids of the destination (a diagonal block: one per group the updates touch; unused: -1)
     const GetrfTask<T>* getrf;
     const int2* getrf_id;   // sync ids of the lower and the upper half
     const PanelTask<T>* panel;
-    const int2* panel_id;   // x: sync id of the panel block, y: sync id of the diagonal half it is solved against
+    const int2* panel_id;   // x: sync id of the panel block
+    const int4* panel_dep;  // sync ids of the diagonal block's groups the solve depends on (unused: -1)
     int* remaining;         // per sync id: SSSSM sub-tasks still to land on the block
     int* done;              // per sync id: 1 once the block is final
     int* pending;           // per sync id: TSTRF/GESSM sub-tasks (16 rows/columns each) still running
@@ -1305,7 +1311,14 @@ mega_kernel(const MegaParams<T> P)
             }
             __threadfence();
             __syncthreads();
-            if (tid == 0) atomicSub(P.remaining + P.dest_id[mt.a], 1);
+            if (tid == 0)
+            {
+                const int4 di = P.dest_id[mt.a];
+                atomicSub(P.remaining + di.x, 1);
+                if (di.y >= 0) atomicSub(P.remaining + di.y, 1);
+                if (di.z >= 0) atomicSub(P.remaining + di.z, 1);
+                if (di.w >= 0) atomicSub(P.remaining + di.w, 1);
+            }
             break;
         }
         case MEGA_GETRF_SMEM:
@@ -1329,7 +1342,7 @@ mega_kernel(const MegaParams<T> P)
                 T* buf = reinterpret_cast<T*>(smem_raw);
                 for (int i = tid; i < 4 * nb; i += 512) buf[i] = zero<T>();
                 __syncthreads();
-                getrf_body<T, 512>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf);
+                getrf_body<T, 512>(nb, G.lower.val, G.lower.ptr, G.lower.idx, G.upper.val, G.upper.ptr, G.upper.idx, buf, G.c0, G.c1);
             }
             if (P.getrf_dd && P.getrf_dd[mt.a] >= 0)
             {
@@ -1350,7 +1363,15 @@ mega_kernel(const MegaParams<T> P)
             const CPanelTask cpt = P.cptasks[mt.a];
             const PanelTask<T> Q = P.panel[cpt.panel];
             const int2 id = P.panel_id[cpt.panel];
-            if (tid == 0) { spin_until_set(P.done + id.y, P.multi); spin_until_zero(P.remaining + id.x); }
+            if (tid == 0)
+            {
+                const int4 dp = P.panel_dep[cpt.panel];
+                spin_until_set(P.done + dp.x, P.multi);
+                if (dp.y >= 0) spin_until_set(P.done + dp.y, P.multi);
+                if (dp.z >= 0) spin_until_set(P.done + dp.z, P.multi);
+                if (dp.w >= 0) spin_until_set(P.done + dp.w, P.multi);
+                spin_until_zero(P.remaining + id.x);
+            }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             panel_compact_cta<T>(smem_raw, nb, Q, P.ops[Q.dense], P.dds[cpt.dd], cpt.r0, cp_state);
@@ -1369,7 +1390,15 @@ mega_kernel(const MegaParams<T> P)
         {
             const PanelTask<T> Q = P.panel[mt.a];
             const int2 id = P.panel_id[mt.a];
-            if (tid == 0) { spin_until_set(P.done + id.y, P.multi); spin_until_zero(P.remaining + id.x); }
+            if (tid == 0)
+            {
+                const int4 dp = P.panel_dep[mt.a];
+                spin_until_set(P.done + dp.x, P.multi);
+                if (dp.y >= 0) spin_until_set(P.done + dp.y, P.multi);
+                if (dp.z >= 0) spin_until_set(P.done + dp.z, P.multi);
+                if (dp.w >= 0) spin_until_set(P.done + dp.w, P.multi);
+                spin_until_zero(P.remaining + id.x);
+            }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             // one task = 64 consecutive rows/columns of the block (four per warp); the diagonal half they are solved

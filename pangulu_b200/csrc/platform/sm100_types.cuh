@@ -112,10 +112,12 @@ struct Blk
 };
 
 // GETRF: lower = strict lower CSC, upper = upper incl. diagonal CSR (diagonal first in each row)
-template <class T> struct GetrfTask { Blk<T> lower, upper; };
+// [c0, c1): the index range of the block to factor (an independent group of the diagonal block; the whole block: 0, nb)
+template <class T> struct GetrfTask { Blk<T> lower, upper; int c0, c1, grp, pad; };
 // TSTRF: b = strictly-lower block (uses its CSR mirror), diag = UPPER half of the diagonal block
 // GESSM: b = upper block (CSC), diag = LOWER half of the diagonal block
 // dense: index of the block's compact dense copy (sm100_compact.cuh) or -1
+// kind: PANGULU_TASK_TSTRF / _GESSM in the low byte, bits 8..11: groups of the diagonal block the solve depends on
 template <class T> struct PanelTask { Blk<T> b, diag; int kind; int dense; };
 // SSSSM: destination (c = the block, or the LOWER half when the destination is a diagonal block;
 // u = UPPER half or null) and the range of (A,B) operand pairs applied to it

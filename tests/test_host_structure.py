@@ -72,7 +72,7 @@ def test_schedule_respects_dependencies(policy):
     update of a destination runs after the wave that finalises it (lazy policy: exactly in that wave)."""
     A = matrices.poisson3d(12)
     nb = 32
-    s = PanguLU(A, nb=nb, host_only=True, schedule=policy)
+    s = PanguLU(A, nb=nb, host_only=True, schedule=policy, split_diag=0)
     try:
         tasks, wave_ptr = s.schedule()
         wave_of_task = np.repeat(np.arange(len(wave_ptr) - 1), np.diff(wave_ptr.astype(np.int64)))
@@ -123,7 +123,7 @@ def test_block_cyclic_ownership_partitions_the_tasks(nproc):
     partition of the single-rank list, and every operand a rank reads is a block it holds."""
     A = matrices.poisson3d(10)
     nb = 32
-    base = PanguLU(A, nb=nb, host_only=True)
+    base = PanguLU(A, nb=nb, host_only=True, split_diag=0)
     t0, _ = base.schedule()
     all_tasks = sorted((int(t["row"]), int(t["col"]), int(t["kernel_id"]), int(t["task_level"])) for t in t0)
     base.finalize()
