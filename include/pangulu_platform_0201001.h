@@ -158,6 +158,9 @@ void pangulu_sm100_plan_add_push(pangulu_sm100_plan *plan, const void *d_value_l
 /* compact dense operand copies (sm100_compact.cuh) across ranks: where the plan keeps them (one allocation, exported
  * with pangulu_sm100_ipc_export), the byte offset of the copy of the block whose device value array is d_value (-1:
  * none), and a push that also writes the owner's copy into the consumer's (peer_dense, peer-mapped; may be NULL) */
+/* work statistics of a plan: "ct_tasks", "ct_pairtiles", "ct_chunks", "ct_dmma" (DMMA instructions of the compact tile
+ * path), "ct_bytes" (operand bytes it streams), "dense_bytes", "dense_blocks" */
+double pangulu_sm100_plan_stat(pangulu_sm100_plan *plan, const char *key);
 void *pangulu_sm100_plan_dense_base(pangulu_sm100_plan *plan, size_t *bytes);
 long long pangulu_sm100_plan_dense_offset(pangulu_sm100_plan *plan, const void *d_value);
 void pangulu_sm100_plan_add_push2(pangulu_sm100_plan *plan, const void *d_value_local, void *peer_value, void *peer_flag, void *peer_dense);

@@ -345,6 +345,7 @@ double pangulu_sm100_driver_info(void* handle, const char* key)
     if (k == "buffer_bytes") return (double)h->B.buf_bytes;
     if (k == "p") return h->B.p;
     if (k == "q") return h->B.q;
+    if (k.rfind("plan_", 0) == 0) return h->plan ? pangulu_sm100_plan_stat(h->plan, k.c_str() + 5) : -1.0;
     if (k.rfind("time_", 0) == 0)
     {
         auto it = h->times.find(k.substr(5));

@@ -557,9 +557,9 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 const size_t nl = lo->columnpointer[G.c1] - cb(lo, G.c0), nu = up->columnpointer[G.c1] - cb(up, G.c0);
                 const size_t need = getrf_smem_bytes(nb, nl, nu);
                 // getrf_mode: 0 auto, 1 never stage in shared memory, 2 never promote to dense, 3 always dense (nb <= 256)
-                const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256 && !grouped;
+                const bool want_dense = g.opt.getrf_mode == 3 && nb <= 256;
                 if (!want_dense && need + 512 <= (size_t)g.max_smem_optin && g.opt.getrf_mode != 1) { fit.push_back(G); fit_smem = std::max(fit_smem, need); fit_slot.push_back(lo); }
-                else if (grouped) { glob.push_back(G); glob_slot.push_back(lo); }   // a group never takes the dense whole-block kernel
+                else if (grouped && (nb > 256 || g.opt.getrf_mode == 2)) { glob.push_back(G); glob_slot.push_back(lo); }
                 else { big.push_back(G); big_slot.push_back(lo); }
                 if (eager_download)
                 {
@@ -954,6 +954,7 @@ struct pangulu_sm100_plan
     std::vector<const void*> op_val;  // per compact copy: device value array of the block it mirrors (sync id key)
     void* diag_dense_buf = nullptr;   // dense triangular copies of diagonal blocks (compact panel path)
     std::unordered_map<const void*, size_t> dense_of_val;  // device value array -> compact copy index
+    double stat_ct_pairtiles = 0, stat_ct_chunks = 0, stat_ct_dmma = 0, stat_ct_abytes = 0, stat_ct_tasks = 0, stat_ct_msum = 0, stat_ct_ntsum = 0;
     size_t dense_total_bytes = 0;
     // persistent executor
     bool mega = false;
@@ -1563,6 +1564,31 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     pl->D.panel = (PanelTask<T>*)(d + b0);
     pl->D.dests = (SsssmDest<T>*)(d + b0 + b1);
     pl->D.pairs = (SsssmPair<T>*)(d + b0 + b1 + b2);
+    {
+        // work statistics of the compact tile path (pangulu_sm100_plan_stat)
+        const DenseReg& R = pl->reg;
+        for (const CTileTask& ct : P.ctasks)
+        {
+            const SsssmDest<T>& D2 = P.dests[ct.dest];
+            pl->stat_ct_tasks += 1;
+            for (u32 pp = D2.pair_begin; pp < D2.pair_end; ++pp)
+            {
+                const DenseReg::Entry& ea = R.entries[P.cpairs[pp].a];
+                const DenseReg::Entry& eb = R.entries[P.cpairs[pp].b];
+                const u16* pre = R.meta.data() + eb.meta_off + eb.cnt + nb;
+                const int nt = pre[ct.chi] - pre[ct.clo];
+                if (nt <= 0) continue;
+                const int ch = __builtin_popcount(ea.kmask & eb.kmask);
+                if (!ch) continue;
+                pl->stat_ct_pairtiles += 1;
+                pl->stat_ct_chunks += ch;
+                pl->stat_ct_dmma += (double)ch * 4.0 * ((ea.cnt + 7) / 8) * ((nt + 7) / 8);
+                pl->stat_ct_abytes += (double)ch * (16.0 * ea.ld + 20.0 * nt) * sizeof(T);
+                pl->stat_ct_msum += ea.cnt;
+                pl->stat_ct_ntsum += nt;
+            }
+        }
+    }
     if (g.opt.executor == 1) build_mega(pl);
     // the host copies of the descriptor arrays are no longer needed; keep only the step list
     std::vector<GetrfTask<T>>().swap(P.getrf);
@@ -1668,6 +1694,27 @@ void pangulu_sm100_plan_add_push2(pangulu_sm100_plan* pl, const void* d_value_lo
 void pangulu_sm100_plan_add_push(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag)
 {
     pangulu_sm100_plan_add_push2(pl, d_value_local, peer_value, peer_flag, nullptr);
+}
+double pangulu_sm100_plan_stat(pangulu_sm100_plan* pl, const char* key)
+{
+    if (!pl || !key) return -1;
+    if (!strcmp(key, "ct_prof_on")) { int one = 1; CK(cudaMemcpyToSymbol(g_ct_prof_on, &one, sizeof one)); unsigned long long z[10] = {0}; CK(cudaMemcpyToSymbol(g_ct_prof, z, sizeof z)); return 0; }
+    if (!strncmp(key, "ct_prof", 7) && key[7] >= '0' && key[7] <= '9')
+    {
+        unsigned long long v[10];
+        CK(cudaMemcpyFromSymbol(v, g_ct_prof, sizeof v));
+        return (double)v[key[7] - '0'];
+    }
+    if (!strcmp(key, "ct_tasks")) return pl->stat_ct_tasks;
+    if (!strcmp(key, "ct_pairtiles")) return pl->stat_ct_pairtiles;
+    if (!strcmp(key, "ct_chunks")) return pl->stat_ct_chunks;
+    if (!strcmp(key, "ct_dmma")) return pl->stat_ct_dmma;
+    if (!strcmp(key, "ct_bytes")) return pl->stat_ct_abytes;
+    if (!strcmp(key, "ct_msum")) return pl->stat_ct_msum;
+    if (!strcmp(key, "ct_ntsum")) return pl->stat_ct_ntsum;
+    if (!strcmp(key, "dense_bytes")) return (double)pl->dense_total_bytes;
+    if (!strcmp(key, "dense_blocks")) return (double)pl->reg.entries.size();
+    return -1;
 }
 void* pangulu_sm100_plan_dense_base(pangulu_sm100_plan* pl, size_t* bytes)
 {

@@ -99,7 +99,7 @@ struct CtLayout
     static constexpr size_t pc_off = acc_bytes + ring_bytes;
     static constexpr size_t pc_bytes = (size_t)PSM_CT_BATCH * 48;
     static constexpr size_t item_off = pc_off + pc_bytes;
-    static constexpr size_t rank_off = item_off + (size_t)PSM_CT_BATCH * 16 * 2;
+    static constexpr size_t rank_off = item_off + (size_t)PSM_CT_BATCH * 16 * 4;
     static constexpr size_t total = rank_off + 256 + 2 * TN + 64;
 };
 
@@ -118,9 +118,53 @@ struct CtPairSm   // one staged operand pair (48 bytes)
 template <class T> struct ct_traits { static constexpr int TN = 32, STAGES = 4; };
 template <> struct ct_traits<pangulu_sm100_c64> { static constexpr int TN = 16, STAGES = 2; };
 
+// DMMA inner products of one k-chunk with compile-time tile counts: the mma.sync instructions sit in straight-line code
+// (a predicated mma.sync costs a WARPSYNC each).  racc layout: [(mt*2 + slot)*2 + h], slot = column tile (tall grid) or
+// k4 parity (small grids).
+template <int TM>
+__device__ __forceinline__ void ct_chunk_small(double* racc, const double* Ap, const double* Bp, int ld)
+{
+#pragma unroll
+    for (int k4 = 0; k4 < PSM_CT_KC; k4 += 4)
+    {
+        const double b = Bp[k4];
+        double a[TM];
+#pragma unroll
+        for (int mt = 0; mt < TM; ++mt) a[mt] = Ap[k4 * ld + mt * 8];
+#pragma unroll
+        for (int mt = 0; mt < TM; ++mt)
+        {
+            const int slot = (k4 >> 2) & 1;
+            dmma884c(racc[(mt * 2 + slot) * 2], racc[(mt * 2 + slot) * 2 + 1], a[mt], b);
+        }
+    }
+}
+template <int TM, int TNC>
+__device__ __forceinline__ void ct_chunk_tall(double* racc, const double* Ap, const double* Bp, int ld)
+{
+#pragma unroll
+    for (int k4 = 0; k4 < PSM_CT_KC; k4 += 4)
+    {
+        double a[TM], b[TNC];
+#pragma unroll
+        for (int mt = 0; mt < TM; ++mt) a[mt] = Ap[k4 * ld + mt * 8];
+#pragma unroll
+        for (int nt2 = 0; nt2 < TNC; ++nt2) b[nt2] = Bp[nt2 * 8 * PSM_CT_BLD + k4];
+#pragma unroll
+        for (int mt = 0; mt < TM; ++mt)
+#pragma unroll
+            for (int nt2 = 0; nt2 < TNC; ++nt2) dmma884c(racc[(mt * 2 + nt2) * 2], racc[(mt * 2 + nt2) * 2 + 1], a[mt], b[nt2]);
+    }
+}
+
 // Barrier state of a CTA that runs many compact-tile tasks (persistent executor): the mbarriers live in static shared
 // memory (other task kinds reuse the dynamic part), are initialised once, and every wait flips the barrier's bit.
 struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
+
+// optional phase profile of the compact tile routine (warp 0 lane 0 of every CTA, clock64): prologue, staging, wait for
+// operands, compute, flush, pair setup, epilogue, produce
+__device__ unsigned long long g_ct_prof[10];
+__device__ int g_ct_prof_on;
 
 // One CTA, one tile of the destination: the block columns [clo, chi).  The host cuts the tiles so that neither the
 // destination nor any B operand queued for it has more than TN NON-EMPTY columns in the range (compact column tiles:
@@ -140,13 +184,20 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     unsigned char* ring = smem_raw + Lay::acc_bytes;
     __shared__ __align__(8) unsigned long long bars[2 * NSLOT];  // [0,NSLOT) full, [NSLOT,2*NSLOT) empty
     CtPairSm* pc = reinterpret_cast<CtPairSm*>(smem_raw + Lay::pc_off);
-    u16* items = reinterpret_cast<u16*>(smem_raw + Lay::item_off);  // (pair_in_batch << 4) | chunk
+    u32* items = reinterpret_cast<u32*>(smem_raw + Lay::item_off);  // (pair_in_batch << 16) | mask of the item's k-chunks (up to 4)
     unsigned char* crank = smem_raw + Lay::rank_off;                // [nb]: position of a column inside this tile, 0xff otherwise
     u16* ccols = reinterpret_cast<u16*>(smem_raw + Lay::rank_off + 256);  // [TN]: the tile's columns
-    __shared__ int s_nitems, s_slot_bytes, s_wcnt[8], s_ntc;
+    __shared__ int s_nitems, s_slot_bytes, s_group, s_wcnt[8], s_ntc;
 
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
     const bool diag = D.u.val != nullptr;
+    // the producer (bulk-copy issue, ~300 cycles per item) is lane 0 of the LAST warp: in the small warp grids that warp
+    // rarely has tensor work, so the issue cost stays off the busy warps
+    constexpr int PTID = 480;
+    const bool prof = g_ct_prof_on != 0 && tid == 0;
+    long long pt = prof ? clock64() : 0;
+    unsigned long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    auto lap = [&](int k) { if (prof) { const long long now = clock64(); pacc[k] += (unsigned long long)(now - pt); pt = now; } };
 
     // ---- task prologue: the tile's columns, a clear accumulator tile, armed barriers
     {
@@ -196,6 +247,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     for (int i = 0; i < NACC; ++i) racc[i] = zero<T>();
     u32 full_bits = st.full_bits, empty_bits = st.empty_bits;
 
+    lap(0);
     for (u32 pb = D.pair_begin; pb < D.pair_end; pb += PSM_CT_BATCH)
     {
         const int npb = (int)min((u32)PSM_CT_BATCH, D.pair_end - pb);
@@ -224,16 +276,22 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 e.kmask = km;
                 if (km) bytes = (int)((KC * A.ld + e.nt * BLD) * sizeof(T));
             }
-            const int cnt = __popc(km);
+            // an item = up to G k-chunks of one pair (one mbarrier hand-over, 2 G bulk copies): G from the largest chunk of
+            // the batch, so that 8 items fit the ring when chunks are small and 4 when they are not
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) bytes = max(bytes, __shfl_xor_sync(PSM_FULL, bytes, o));
+            const int chunk_bytes = max(128, (bytes + 127) & ~127);
+            const int slot8 = (int)(Lay::ring_bytes / NSLOT), slot4 = (int)(Lay::ring_bytes / (MAXST >= 4 ? 4 : 2));
+            const int G = chunk_bytes <= slot8 ? min(4, slot8 / chunk_bytes) : min(4, max(1, slot4 / chunk_bytes));
+            const int cnt = (__popc(km) + G - 1) / G;   // items of this lane's pair
             int off = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
             {
                 const int v = __shfl_up_sync(PSM_FULL, off, o);
                 if (lane >= o) off += v;
-                bytes = max(bytes, __shfl_xor_sync(PSM_FULL, bytes, o));
             }
-            if (lane == 31) { s_nitems = off; s_slot_bytes = (bytes + 127) & ~127; }
+            if (lane == 31) { s_nitems = off; s_slot_bytes = G * chunk_bytes; s_group = G; }
             off -= cnt;
             if (lane < npb)
             {
@@ -242,19 +300,22 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 u32 k = km;
                 while (k)
                 {
-                    const int c = __ffs(k) - 1;
-                    k &= k - 1;
-                    items[off++] = (u16)((lane << 4) | c);
+                    u32 m = 0;
+                    for (int q = 0; q < G && k; ++q) { m |= k & (0u - k); k &= k - 1; }
+                    items[off++] = ((u32)lane << 16) | m;
                 }
             }
         }
         __syncthreads();
+        lap(1);
         const int nitems = s_nitems;
         if (nitems == 0) continue;
-        const int slot_bytes = s_slot_bytes;
-        // pipeline depth: 8 slots when the batch's largest item fits an eighth of the ring, else 4 (>= MAXST by construction)
+        const int slot_bytes = s_slot_bytes, G = s_group;
+        // pipeline depth: 8 slots when the batch's items fit an eighth of the ring, else 4 (>= MAXST by construction)
         const int nst = ((size_t)slot_bytes * NSLOT <= Lay::ring_bytes) ? NSLOT : (MAXST >= 4 ? 4 : 2);
-        const int smask = nst - 1, LA = nst - 1;
+        // look-ahead nst-2, not nst-1: the slot a new item overwrites was released one full item earlier, so the producer
+        // (a lane of warp 0, which also computes) never waits for the slowest warp of the item just consumed
+        const int smask = nst - 1, LA = nst > 2 ? nst - 2 : 1;
 
         u16 rfull[4] = {0xffff, 0xffff, 0xffff, 0xffff}, cfull[4] = {0xffff, 0xffff, 0xffff, 0xffff};
         u16 rf8[8];
@@ -323,27 +384,40 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         // producer step (thread 0): bulk copies of item i into its slot
         auto produce = [&](int i) {
             const int s = i & smask;
+            lap(7);
             if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
-            const u16 it = items[i];
-            const CtPairSm& e = pc[it >> 4];
-            const int ch = it & 15;
+            lap(8);
+            const u32 it = items[i];
+            const CtPairSm& e = pc[it >> 16];
+            u32 m = it & 0xffffu;
             unsigned char* sb = ring + (size_t)s * slot_bytes;
             const u32 abytes = (u32)(KC * e.ld * sizeof(T)), bbytes = (u32)(e.nt * BLD * sizeof(T));
-            mbar_expect_tx(bars + s, abytes + bbytes);
-            bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
-            bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
+            mbar_expect_tx(bars + s, (u32)__popc(m) * (abytes + bbytes));
+            while (m)
+            {
+                const int ch = __ffs(m) - 1;
+                m &= m - 1;
+                bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
+                bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
+                sb += abytes + bbytes;
+            }
+            lap(9);
         };
-        if (tid == 0)
+        if (tid == PTID)
             for (int i = 0; i < min(LA, nitems); ++i) produce(i);
+        lap(7);
 
         // ---- pairs of the batch; items of a pair are consecutive in the item list
         int ci = 0;
         for (int pl = 0; pl < npb; ++pl)
         {
             const CtPairSm& e = pc[pl];
-            const int cnt = __popc(e.kmask);
+            const int nchunk = __popc(e.kmask);
+            const int cnt = (nchunk + G - 1) / G;   // items of this pair
             if (cnt == 0) continue;
+            lap(3);
             if (have_prev) flush();
+            lap(4);
             have_prev = true;
             cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
             bool active;
@@ -361,11 +435,16 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 }
                 else
                 {
-                    const int tm = MT > 8 ? 4 : MT > 4 ? 2 : 1;
+                    const int tm = (MT + 3) / 4;   // m-tiles per row group: the four groups (= SM sub-partitions) get equal shares
                     m_base = (warp & 3) * tm * 8; n_base = (warp >> 2) * 8;
                     mtc = min(tm, max(0, (mpad - m_base) / 8));
                     ntc = cur_nt > n_base ? 1 : 0;
                 }
+                // make the tile counts provably warp-uniform (vote results live in uniform registers): otherwise every
+                // predicated mma.sync is preceded by a WARPSYNC
+                mtc = __popc(__ballot_sync(PSM_FULL, lane < mtc));
+                ntc = __popc(__ballot_sync(PSM_FULL, lane < ntc));
+                small = __all_sync(PSM_FULL, small);
                 active = mtc > 0 && ntc > 0;
                 if (active)
                 {
@@ -412,53 +491,48 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 }
             }
             const bool warp_active = __any_sync(PSM_FULL, active);
+            lap(5);
             for (int j = 0; j < cnt; ++j, ++ci)
             {
-                if (tid == 0 && ci + LA < nitems) produce(ci + LA);
+                if (tid == PTID && ci + LA < nitems) produce(ci + LA);
+                lap(7);
                 const int s = ci & smask;
                 mbar_wait(bars + s, (full_bits >> s) & 1u);
                 full_bits ^= 1u << s;
+                lap(2);
+                const int nch = min(G, nchunk - j * G);   // chunks in this item
                 if (warp_active)
-                {
-                    const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes);
+                  for (int q = 0; q < nch; ++q)
+                  {
+                    const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes) + (size_t)q * (KC * cur_ld + cur_nt * BLD);
                     const T* Bs = As + KC * cur_ld;
                     if constexpr (kDouble)
                     {
                         const double* Ap = As + lk * cur_ld + m_base + lr;
                         const double* Bp = Bs + (n_base + lr) * BLD + lk;
+                        double* ra = reinterpret_cast<double*>(racc);
                         if (small)
                         {
-#pragma unroll
-                            for (int k4 = 0; k4 < KC; k4 += 4)
+                            switch (mtc)
                             {
-                                const double b = Bp[k4];
-#pragma unroll
-                                for (int mt = 0; mt < 4; ++mt)
-                                    if (mt < mtc)
-                                    {
-                                        const double a = Ap[k4 * cur_ld + mt * 8];
-                                        if ((k4 >> 2) & 1) dmma884c(racc[(mt * 2 + 1) * 2], racc[(mt * 2 + 1) * 2 + 1], a, b);
-                                        else dmma884c(racc[(mt * 2) * 2], racc[(mt * 2) * 2 + 1], a, b);
-                                    }
+                            case 1: ct_chunk_small<1>(ra, Ap, Bp, cur_ld); break;
+                            case 2: ct_chunk_small<2>(ra, Ap, Bp, cur_ld); break;
+                            case 3: ct_chunk_small<3>(ra, Ap, Bp, cur_ld); break;
+                            default: ct_chunk_small<4>(ra, Ap, Bp, cur_ld); break;
                             }
                         }
                         else
                         {
-#pragma unroll
-                            for (int k4 = 0; k4 < KC; k4 += 4)
+                            switch (mtc * 2 + ntc)
                             {
-                                double a[4], b[2];
-#pragma unroll
-                                for (int mt = 0; mt < 4; ++mt) a[mt] = mt < mtc ? Ap[k4 * cur_ld + mt * 8] : 0.0;
-                                b[0] = Bp[k4];
-                                b[1] = ntc > 1 ? Bp[8 * BLD + k4] : 0.0;
-#pragma unroll
-                                for (int mt = 0; mt < 4; ++mt)
-                                    if (mt < mtc)
-                                    {
-                                        dmma884c(racc[(mt * 2) * 2], racc[(mt * 2) * 2 + 1], a[mt], b[0]);
-                                        if (ntc > 1) dmma884c(racc[(mt * 2 + 1) * 2], racc[(mt * 2 + 1) * 2 + 1], a[mt], b[1]);
-                                    }
+                            case 3: ct_chunk_tall<1, 1>(ra, Ap, Bp, cur_ld); break;
+                            case 4: ct_chunk_tall<1, 2>(ra, Ap, Bp, cur_ld); break;
+                            case 5: ct_chunk_tall<2, 1>(ra, Ap, Bp, cur_ld); break;
+                            case 6: ct_chunk_tall<2, 2>(ra, Ap, Bp, cur_ld); break;
+                            case 7: ct_chunk_tall<3, 1>(ra, Ap, Bp, cur_ld); break;
+                            case 8: ct_chunk_tall<3, 2>(ra, Ap, Bp, cur_ld); break;
+                            case 9: ct_chunk_tall<4, 1>(ra, Ap, Bp, cur_ld); break;
+                            default: ct_chunk_tall<4, 2>(ra, Ap, Bp, cur_ld); break;
                             }
                         }
                     }
@@ -484,14 +558,16 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                             }
                         }
                     }
-                    __syncwarp();
-                }
+                  }
+                if (warp_active) __syncwarp();
                 if (lane == 0) mbar_arrive(bars + NSLOT + s);
             }
         }
+        lap(3);
         if (have_prev) flush();
+        lap(4);
         // every release must be matched by a wait of the producer, so the barrier bits stay in step
-        if (tid == 0)
+        if (tid == PTID)
             for (int j = max(0, nitems - nst); j < nitems; ++j)
             {
                 const int s = j & smask;
@@ -501,6 +577,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     }
     st.full_bits = full_bits;
     st.empty_bits = empty_bits;
+    lap(4);
 
     // ---- epilogue: accumulator tile -> destination pattern (other CTAs may update the same block: reductions)
     __syncthreads();
@@ -540,6 +617,9 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         }
     }
     __syncthreads();  // the accumulator tile is free again
+    lap(6);
+    if (prof)
+        for (int k = 0; k < 10; ++k) atomicAdd(&g_ct_prof[k], pacc[k]);
 }
 
 // stand-alone launch (per-wave executor): one CTA per tile task

@@ -446,10 +446,13 @@ getrf_smem_kernel(int nb, const GetrfTask<T>* __restrict__ tasks)
 //   smem = 2 * 16 * nbp * sizeof(T) + 64 * sizeof(T), nbp = nb rounded up to 32;  scratch = nbp*nbp*sizeof(T) per task
 #define PSM_GETRF_W 16
 template <class T, int THREADS>
-__device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb, const GetrfTask<T>& G, T* __restrict__ Tm)
+__device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_block, const GetrfTask<T>& G, T* __restrict__ Tm)
 {
     constexpr int W = PSM_GETRF_W;
     constexpr int NW = THREADS / PSM_WARP;
+    // the task's group [c0, c1) of the block is factored as a dense nb x nb matrix in LOCAL coordinates (index - off)
+    (void)nb_block;
+    const int off = G.c0, nb = G.c1 - G.c0;
     const int nbp = (nb + 31) & ~31;
     T* Ls = reinterpret_cast<T*>(smem_raw);   // [W][nbp]  L panel (rows >= j0)
     T* Us = Ls + W * nbp;                     // [W][nbp]  U12 rows of the panel
@@ -462,8 +465,8 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb,
     __syncthreads();
     for (int c = warp; c < nb; c += NW)
     {
-        for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)c * nbp + Lo.idx[e]] = Lo.val[e];
-        for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Tm[(size_t)Up.idx[e] * nbp + c] = Up.val[e];  // row c of U
+        for (u32 e = col_begin(Lo.ptr, off + c) + lane; e < Lo.ptr[off + c + 1]; e += PSM_WARP) Tm[(size_t)c * nbp + (Lo.idx[e] - off)] = Lo.val[e];
+        for (u32 e = col_begin(Up.ptr, off + c) + lane; e < Up.ptr[off + c + 1]; e += PSM_WARP) Tm[(size_t)(Up.idx[e] - off) * nbp + c] = Up.val[e];  // row c of U
     }
     __syncthreads();
 
@@ -566,8 +569,8 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb,
     // ---- gather the pattern back
     for (int c = warp; c < nb; c += NW)
     {
-        for (u32 e = col_begin(Lo.ptr, c) + lane; e < Lo.ptr[c + 1]; e += PSM_WARP) Lo.val[e] = Tm[(size_t)c * nbp + Lo.idx[e]];
-        for (u32 e = col_begin(Up.ptr, c) + lane; e < Up.ptr[c + 1]; e += PSM_WARP) Up.val[e] = Tm[(size_t)Up.idx[e] * nbp + c];
+        for (u32 e = col_begin(Lo.ptr, off + c) + lane; e < Lo.ptr[off + c + 1]; e += PSM_WARP) Lo.val[e] = Tm[(size_t)c * nbp + (Lo.idx[e] - off)];
+        for (u32 e = col_begin(Up.ptr, off + c) + lane; e < Up.ptr[off + c + 1]; e += PSM_WARP) Up.val[e] = Tm[(size_t)(Up.idx[e] - off) * nbp + c];
     }
 }
 

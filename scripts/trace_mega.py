@@ -13,7 +13,9 @@ L.pangulu_sm100_set_option(b"trace", 1); L.pangulu_sm100_set_option(b"executor",
 for kv in a.opt:
     k, v = kv.split("="); assert L.pangulu_sm100_set_option(k.encode(), int(v)) == 0
 s = PanguLU(matrices.poisson3d(a.size), nb=a.nb, mode=1, schedule=a.schedule, lookahead=a.lookahead)
-s.gstrf(); s.reset_values(True); t = s.gstrf()
+s.gstrf(); s.reset_values(True)
+if os.environ.get('CT_PROF'): s.info('plan_ct_prof_on')
+t = s.gstrf()
 n = L.pangulu_sm100_driver_trace(s._h, None, 0)
 buf = np.zeros((n, 4), dtype=np.uint64)
 L.pangulu_sm100_driver_trace(s._h, buf.ctypes.data, n)
@@ -29,6 +31,16 @@ for k in range(8):
     if m.any():
         run, wait = end[m] - start[m], start[m] - fetch[m]
         print(f"{names[k]:12s} n={m.sum():7d} run total {run.sum()/1e3:9.1f} ms mean {run.mean():8.1f} us max {run.max():9.1f} | wait total {wait.sum()/1e3:9.1f} ms mean {wait.mean():8.1f} us")
+st = {k: s.info("plan_" + k) for k in ("ct_tasks", "ct_pairtiles", "ct_chunks", "ct_dmma", "ct_bytes", "ct_msum", "ct_ntsum", "dense_bytes", "dense_blocks")}
+if st["ct_pairtiles"] > 0:
+    print("compact tiles: tasks %.0f pair-tiles %.0f chunks/pair-tile %.2f mean m' %.1f mean nt %.1f | DMMA %.3e -> %.1f CTA-s at 16.1 cyc | operand bytes %.3e | dense copies %.0f blocks %.2f GB"
+          % (st["ct_tasks"], st["ct_pairtiles"], st["ct_chunks"] / st["ct_pairtiles"], st["ct_msum"] / st["ct_pairtiles"], st["ct_ntsum"] / st["ct_pairtiles"],
+             st["ct_dmma"], st["ct_dmma"] * 16.1 / 4 / 1.965e9, st["ct_bytes"], st["dense_blocks"], st["dense_bytes"] / 1e9))
+if os.environ.get('CT_PROF'):
+    names7 = ["prologue", "staging", "wait_operands", "compute", "flush", "pair_setup", "epilogue", "other", "producer_wait_slot", "producer_issue"]
+    v = [s.info("plan_ct_prof%d" % k) for k in range(10)]
+    tot = sum(v)
+    print("compact tile phases (warp 0, cycles): " + "  ".join(f"{n} {x/tot*100:.1f}%" for n, x in zip(names7, v)) + f"  total {tot/1.965e9:.1f} CTA-s")
 print(f"flop {s.info('flop'):.4e}  -> {s.info('flop')/t/1e9:.1f} GFLOP/s")
 for k in (0, 6):
     m = kind == k
