@@ -61,7 +61,7 @@ struct Options
     long long trace = 0;        // persistent executor: record per-task fetch/start/end timestamps (pangulu_sm100_plan_trace)
     long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
     long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
-    long long compact_threshold = 10;  // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path ...
+    long long compact_threshold = 2;   // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path ...
     long long compact_block_threshold = 1;  // ... if both blocks have nnz/nb^2 >= this (per mille): the block-level rule decides who gets a compact copy
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
