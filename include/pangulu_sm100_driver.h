@@ -92,6 +92,8 @@ long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *h
 void pangulu_sm100_driver_commit(void *handle);
 void pangulu_sm100_driver_gstrf_reset(void *handle);
 void pangulu_sm100_driver_gstrf_launch(void *handle);
+/* independent groups of diagonal block k: bounds[0..ng] of the index ranges, returns ng (1 = not split) */
+int pangulu_sm100_driver_diag_groups(void *handle, long long k, unsigned short *bounds5);
 /* drop and rebuild the device-resident plan with the platform options in force now (e.g. "trace") */
 void pangulu_sm100_driver_rebuild_plan(void *handle);
 /* task trace of the last resident gstrf (see pangulu_sm100_plan_trace) */

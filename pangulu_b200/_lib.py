@@ -44,7 +44,7 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_trace", "pangulu_sm100_driver_set_barrier", "pangulu_sm100_driver_ipc_handles",
     "pangulu_sm100_driver_mirror_table", "pangulu_sm100_driver_connect_peer", "pangulu_sm100_driver_commit",
     "pangulu_sm100_driver_gstrf_reset", "pangulu_sm100_driver_gstrf_launch", "pangulu_sm100_driver_set_mode",
-    "pangulu_sm100_driver_rebuild_plan",
+    "pangulu_sm100_driver_rebuild_plan", "pangulu_sm100_driver_diag_groups",
 ]
 
 
@@ -169,6 +169,8 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_driver_commit.argtypes = [vp]
     L.pangulu_sm100_driver_set_mode.argtypes = [vp, C.c_int]
     L.pangulu_sm100_driver_rebuild_plan.argtypes = [vp]
+    L.pangulu_sm100_driver_diag_groups.argtypes = [vp, C.c_longlong, vp]
+    L.pangulu_sm100_driver_diag_groups.restype = C.c_int
     L.pangulu_sm100_driver_gstrf_reset.argtypes = [vp]
     L.pangulu_sm100_driver_gstrf_launch.argtypes = [vp]
     L.pangulu_sm100_driver_trace.argtypes = [vp, vp, C.c_longlong]

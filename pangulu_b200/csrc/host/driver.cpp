@@ -382,6 +382,16 @@ const pangulu_task_t* pangulu_sm100_driver_tasks(void* handle, const pangulu_uin
     return h->sched.tasks.data();
 }
 
+// groups of diagonal block k (schedule.cpp: diag_groups): writes bounds[0..ng] (ng <= 4) and returns ng
+int pangulu_sm100_driver_diag_groups(void* handle, long long k, unsigned short* bounds5)
+{
+    Handle* h = (Handle*)handle;
+    if (k < 0 || (size_t)k >= h->sched.group_count.size()) return 0;
+    const int ng = h->sched.group_count[k];
+    for (int g = 0; g <= ng; ++g) bounds5[g] = h->sched.group_bounds[(size_t)k * (DIAG_MAX_GROUPS + 1) + g];
+    return ng;
+}
+
 void pangulu_sm100_driver_set_mode(void* handle, int mode) { ((Handle*)handle)->mode = mode; }
 
 // drop the device-resident plan and build it again with the platform options in force now (e.g. "trace")

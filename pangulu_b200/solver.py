@@ -156,6 +156,12 @@ class PanguLU:
         dist.barrier(group)
         return made
 
+    def diag_groups(self, k: int) -> list[int]:
+        """Index bounds of the independent groups of diagonal block k ([0, nb] when it is not split)."""
+        b = (C.c_ushort * 5)()
+        ng = int(self.L.pangulu_sm100_driver_diag_groups(self._h, int(k), b))
+        return [int(b[i]) for i in range(ng + 1)]
+
     def factor_check(self) -> float:
         return float(self.L.pangulu_sm100_driver_factor_check(self._h))
 

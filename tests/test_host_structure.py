@@ -138,3 +138,59 @@ def test_block_cyclic_ownership_partitions_the_tasks(nproc):
         got += [(int(x["row"]), int(x["col"]), int(x["kernel_id"]), int(x["task_level"])) for x in t]
         s.finalize()
     assert sorted(got) == all_tasks
+
+
+def test_diagonal_groups_schedule():
+    """Independent groups of diagonal blocks (schedule.cpp: diag_groups): the groups partition the block, the filled
+    pattern is block diagonal over them, every group has its own GETRF task, the total work is unchanged, every task
+    still runs after what it depends on, and the dependency depth shrinks."""
+    A = matrices.poisson3d(14)
+    nb = 32
+    whole = PanguLU(A, nb=nb, host_only=True, split_diag=0)
+    split = PanguLU(A, nb=nb, host_only=True, split_diag=1)
+    try:
+        assert split.info("flop") == whole.info("flop")
+        assert split.info("n_ssssm") == whole.info("n_ssssm") and split.info("n_tstrf") == whole.info("n_tstrf")
+        assert split.info("n_split_diag") > 0 and split.info("nwave") < whole.info("nwave")
+        bl = int(split.info("block_length"))
+        groups = {k: split.diag_groups(k) for k in range(bl)}
+        lower = {b.brow: b for b in split.blocks(copy=True) if b.brow == b.bcol and not b.is_upper}
+        offdiag = {(b.brow, b.bcol): b for b in split.blocks(copy=True) if b.brow != b.bcol}
+        ngetrf = 0
+        for k, bd in groups.items():
+            assert bd[0] == 0 and bd[-1] == nb and all(x < y for x, y in zip(bd, bd[1:])) and len(bd) <= 5
+            ngetrf += len(bd) - 1
+            grp = np.searchsorted(np.array(bd), np.arange(nb), side="right") - 1
+            b = lower[k]
+            cols = np.repeat(np.arange(nb), np.diff(b.colptr.astype(np.int64)))
+            assert np.array_equal(grp[b.rowidx], grp[cols]), f"diagonal block {k} is not block diagonal over its groups"
+        assert ngetrf == int(split.info("n_getrf"))
+        tasks, wave_ptr = split.schedule()
+        wave = np.repeat(np.arange(len(wave_ptr) - 1), np.diff(wave_ptr.astype(np.int64)))
+        getrf_wave = {}
+        for t, w in zip(tasks, wave):
+            if t["kernel_id"] == _lib.TASK_GETRF:
+                getrf_wave[(int(t["row"]), int(t["compare_flag"]) >> 32)] = w
+        assert len(getrf_wave) == ngetrf
+        grp_of = lambda k, idx: np.unique(np.searchsorted(np.array(groups[k]), idx, side="right") - 1)
+        checked = 0
+        for t, w in zip(tasks, wave):
+            kid, i, j, k = int(t["kernel_id"]), int(t["row"]), int(t["col"]), int(t["task_level"])
+            if kid == _lib.TASK_TSTRF:       # block (i,k): groups of k in which it has columns
+                b = offdiag[(i, j)]
+                touched = grp_of(j, np.nonzero(np.diff(b.colptr.astype(np.int64)))[0])
+                assert all(getrf_wave[(j, int(g))] < w for g in touched)
+                checked += 1
+            elif kid == _lib.TASK_GESSM:     # block (k,j): groups of k in which it has rows
+                b = offdiag[(i, j)]
+                touched = grp_of(i, np.unique(b.rowidx))
+                assert all(getrf_wave[(i, int(g))] < w for g in touched)
+                checked += 1
+            elif kid == _lib.TASK_SSSSM and i == j:   # update of diagonal block i from level k: groups in which L(i,k) has rows
+                touched = grp_of(i, np.unique(offdiag[(i, k)].rowidx))
+                assert all(w <= getrf_wave[(i, int(g))] for g in touched)
+                checked += 1
+        assert checked > 0
+    finally:
+        whole.finalize()
+        split.finalize()
