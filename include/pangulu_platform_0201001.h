@@ -164,6 +164,12 @@ double pangulu_sm100_plan_stat(pangulu_sm100_plan *plan, const char *key);
 void *pangulu_sm100_plan_dense_base(pangulu_sm100_plan *plan, size_t *bytes);
 long long pangulu_sm100_plan_dense_offset(pangulu_sm100_plan *plan, const void *d_value);
 void pangulu_sm100_plan_add_push2(pangulu_sm100_plan *plan, const void *d_value_local, void *peer_value, void *peer_flag, void *peer_dense);
+/* the same per independent group of a diagonal half (pangulu_sm100_set_diag_groups): flag of group `group`, and a push
+ * of the entries [off, off+cnt) of the half's value array when that group's GETRF task is done */
+long long pangulu_sm100_plan_flag_offset2(pangulu_sm100_plan *plan, const void *d_value, int group);
+void pangulu_sm100_plan_expect_remote2(pangulu_sm100_plan *plan, const void *d_value, int group);
+void pangulu_sm100_plan_add_push3(pangulu_sm100_plan *plan, const void *d_value_local, int group, unsigned int off, unsigned int cnt,
+                                  void *peer_value, void *peer_flag);
 void pangulu_sm100_plan_commit(pangulu_sm100_plan *plan);
 void pangulu_sm100_plan_reset(pangulu_sm100_plan *plan);
 void pangulu_sm100_plan_launch(pangulu_sm100_plan *plan);

@@ -34,6 +34,7 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_plan_add_push", "pangulu_sm100_plan_commit", "pangulu_sm100_plan_reset", "pangulu_sm100_plan_launch",
     "pangulu_sm100_ipc_export", "pangulu_sm100_ipc_open", "pangulu_sm100_plan_dense_base", "pangulu_sm100_plan_dense_offset",
     "pangulu_sm100_plan_add_push2", "pangulu_sm100_set_diag_groups", "pangulu_sm100_plan_stat",
+    "pangulu_sm100_plan_flag_offset2", "pangulu_sm100_plan_expect_remote2", "pangulu_sm100_plan_add_push3",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [

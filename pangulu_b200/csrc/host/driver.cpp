@@ -157,12 +157,13 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     t0 = wall_seconds();
     build_blocks(h->A_reordered, h->S, h->nb, (int)g_cfg.rank, (int)g_cfg.nproc, h->B);
     h->times["blocks"] = wall_seconds() - t0;
-    // the element-level pattern is not needed after blocking
-    std::vector<eidx>().swap(h->S.idx);
     t0 = wall_seconds();
     h->sched.policy = (int)g_cfg.schedule;
     h->sched.lookahead = (int)g_cfg.lookahead;
     h->sched.split_diag = (int)g_cfg.split_diag;
+    diag_groups(h->B, h->S, h->sched);
+    // the element-level pattern is not needed any more
+    std::vector<eidx>().swap(h->S.idx);
     build_schedule(h->B, h->sched);
     if (!h->B.host_only)
         for (eidx k = 0; k < h->B.block_length; ++k)
@@ -453,9 +454,9 @@ void pangulu_sm100_driver_ipc_handles(void* handle, unsigned char* out192)
     if (dense && bytes) pangulu_sm100_ipc_export(dense, out192 + 128);
 }
 
-// One row of 6 int64 per remote block this rank mirrors AND reads: {brow, bcol, kind (0 off-diagonal, 1 lower half,
+// One row of 7 int64 per remote block (per independent group, for the halves of a diagonal block) this rank mirrors AND reads: {brow, bcol, kind (0 off-diagonal, 1 lower half,
 // 2 upper half of a diagonal block), byte offset of its value array in the block buffer, byte offset of its done flag
-// in the plan's synchronisation buffer, byte offset of its compact dense copy in the plan's dense buffer or -1}.
+// in the plan's synchronisation buffer, byte offset of its compact dense copy in the plan's dense buffer or -1, group or -1}.
 // Also tells the plan that these blocks arrive from a peer.
 long long pangulu_sm100_driver_mirror_table(void* handle, long long* out, long long cap)
 {
@@ -466,24 +467,30 @@ long long pangulu_sm100_driver_mirror_table(void* handle, long long* out, long l
     for (const pangulu_storage_slot_t& s : B.slots)
     {
         if (s.bin_id == 0) continue;
-        long long flag = -1;
-        if (!B.host_only)
+        const bool is_diag = s.brow_pos == s.bcol_pos;
+        const int ng = is_diag ? h->sched.group_count[s.brow_pos] : 1;
+        for (int g = 0; g < ng; ++g)
         {
-            flag = pangulu_sm100_plan_flag_offset(h->plan, s.d_value);
-            if (flag < 0) continue;  // mirrored but never read by a task of this rank
-            pangulu_sm100_plan_expect_remote(h->plan, s.d_value);
+            long long flag = -1;
+            if (!B.host_only)
+            {
+                flag = pangulu_sm100_plan_flag_offset2(h->plan, s.d_value, g);
+                if (flag < 0) continue;  // mirrored but never read by a task of this rank
+                pangulu_sm100_plan_expect_remote2(h->plan, s.d_value, g);
+            }
+            if (out && n < cap)
+            {
+                long long* r = out + 7 * n;
+                r[0] = s.brow_pos;
+                r[1] = s.bcol_pos;
+                r[2] = !is_diag ? 0 : (s.is_upper ? 2 : 1);
+                r[3] = (long long)((char*)s.d_value - B.d_buf);
+                r[4] = flag;
+                r[5] = (B.host_only || is_diag) ? -1 : pangulu_sm100_plan_dense_offset(h->plan, s.d_value);
+                r[6] = is_diag ? g : -1;   // independent group of the diagonal half (-1: a whole off-diagonal block)
+            }
+            ++n;
         }
-        if (out && n < cap)
-        {
-            long long* r = out + 6 * n;
-            r[0] = s.brow_pos;
-            r[1] = s.bcol_pos;
-            r[2] = s.brow_pos != s.bcol_pos ? 0 : (s.is_upper ? 2 : 1);
-            r[3] = (long long)((char*)s.d_value - B.d_buf);
-            r[4] = flag;
-            r[5] = B.host_only ? -1 : pangulu_sm100_plan_dense_offset(h->plan, s.d_value);
-        }
-        ++n;
     }
     return n;
 }
@@ -501,13 +508,13 @@ long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* h
         pangulu_sm100_ipc_open(handles128, (void**)&peer_buf);
         pangulu_sm100_ipc_open(handles128 + 64, (void**)&peer_sync);
         bool any_dense = false;
-        for (long long i = 0; i < n; ++i) any_dense = any_dense || table[6 * i + 5] >= 0;
+        for (long long i = 0; i < n; ++i) any_dense = any_dense || table[7 * i + 5] >= 0;
         if (any_dense) pangulu_sm100_ipc_open(handles128 + 128, (void**)&peer_dense);
     }
     long long made = 0;
     for (long long i = 0; i < n; ++i)
     {
-        const long long* r = table + 6 * i;
+        const long long* r = table + 7 * i;
         const eidx brow = (eidx)r[0], bcol = (eidx)r[1];
         if (B.owner(brow, bcol) != B.rank) continue;
         int64_t slot = -1;
@@ -526,7 +533,20 @@ long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* h
             fprintf(stderr, "[PanguLU ERROR] peer asks for block (%u,%u) that rank %d owns but does not hold\n", brow, bcol, B.rank);
             exit(EXIT_FAILURE);
         }
-        if (!B.host_only) pangulu_sm100_plan_add_push2(h->plan, B.slots[slot].d_value, peer_buf + r[3], peer_sync + r[4], r[5] >= 0 ? peer_dense + r[5] : nullptr);
+        if (!B.host_only)
+        {
+            if (r[6] >= 0)
+            {
+                // one independent group of a diagonal half: its entries are a contiguous range of the value array
+                const pangulu_storage_slot_t& sl = B.slots[slot];
+                const uint16_t* bd = &h->sched.group_bounds[(size_t)brow * (DIAG_MAX_GROUPS + 1)];
+                const int g = (int)r[6];
+                const unsigned off = sl.columnpointer[bd[g]], end = sl.columnpointer[bd[g + 1]];
+                pangulu_sm100_plan_add_push3(h->plan, sl.d_value, g, off, end - off, peer_buf + r[3], peer_sync + r[4]);
+            }
+            else
+                pangulu_sm100_plan_add_push2(h->plan, B.slots[slot].d_value, peer_buf + r[3], peer_sync + r[4], r[5] >= 0 ? peer_dense + r[5] : nullptr);
+        }
         ++made;
     }
     return made;

@@ -132,6 +132,8 @@ struct Schedule
     int policy = 2;                     // 0 lazy (updates in the destination's wave), 1 eager (as soon as operands are final), 2 windowed
     int lookahead = 6;                  // policy 2: waves before the destination's finalisation at which slack updates run
 };
+// independent groups of the diagonal blocks, from the element-level symbolic pattern (call before build_schedule)
+void diag_groups(const BlockStore& B, const Symbolic& Sy, Schedule& S);
 void build_schedule(BlockStore& B, Schedule& S);
 
 // ---- flop / byte models (reference: src/pangulu_kernel_interface.c:4-176) ----

@@ -41,9 +41,11 @@ struct Proto
 // at the index positions where its filled pattern is block diagonal, adjacent pieces are merged while they agree on
 // "receives updates from earlier block columns" (at most DIAG_MAX_GROUPS groups), and GETRF, the dependency counters
 // of the updates and the waits of the panel solves work per GROUP.  Storage and kernels' arithmetic are unchanged.
-void diag_groups(const BlockStore& B, Schedule& S)
+void diag_groups(const BlockStore& B, const Symbolic& Sy, Schedule& S)
 {
-    const eidx bl = B.block_length;
+    // Works on the element-level symbolic pattern (column c of L: rows >= c, ascending), which every rank computes
+    // itself: the result does not depend on which blocks a rank holds.
+    const eidx bl = B.block_length, n = B.n;
     const int nb = B.nb;
     const size_t nblk = B.bcol_ptr[bl];
     S.group_bounds.assign((size_t)bl * (DIAG_MAX_GROUPS + 1), (uint16_t)nb);
@@ -51,47 +53,48 @@ void diag_groups(const BlockStore& B, Schedule& S)
     S.colgroups.assign(nblk, 1);
     S.rowgroups.assign(nblk, 1);
     for (eidx k = 0; k < bl; ++k) S.group_bounds[(size_t)k * (DIAG_MAX_GROUPS + 1)] = 0;
-    if (!S.split_diag || B.nproc > 1) return;
-    // 1. components: split points p with no entry (r, c), r >= p > c, in the strict lower half
+    if (!S.split_diag || Sy.idx.empty()) return;
+    std::fill(S.colgroups.begin(), S.colgroups.end(), 0);
+    std::fill(S.rowgroups.begin(), S.rowgroups.end(), 0);
+    // 1. components: split points p with no entry (r, c), r >= p > c, inside the diagonal block
     std::vector<std::vector<uint16_t>> comp_start(bl);
-    std::vector<std::vector<uint8_t>> comp_of(bl);   // index -> component (capped at 255 components)
+    std::vector<uint8_t> comp_of((size_t)bl * nb, 0);   // index -> component of its diagonal block (capped at 255)
 #pragma omp parallel for schedule(dynamic, 16)
     for (int64_t k = 0; k < (int64_t)bl; ++k)
     {
-        const int64_t ds = B.slot_of_diag[k];
         std::vector<uint16_t>& st = comp_start[k];
         st.push_back(0);
-        comp_of[k].assign((size_t)nb, 0);
-        if (ds < 0) continue;
-        const pangulu_storage_slot_t& lo = B.slots[ds];
-        int reach = 0;  // largest row index touched by the columns seen so far
-        for (int c = 0; c < nb; ++c)
+        const eidx c0 = (eidx)k * nb, r1 = c0 + nb;
+        int reach = 0;  // largest local row index touched by the columns seen so far
+        for (int cl = 0; cl < nb; ++cl)
         {
-            if (c > 0 && reach < c && st.size() < 255) st.push_back((uint16_t)c);
-            reach = std::max(reach, c);
-            const iptr e1 = lo.columnpointer[c + 1];
-            if (e1 > lo.columnpointer[c]) reach = std::max(reach, (int)lo.rowindex[e1 - 1]);  // rows ascending
-            comp_of[k][c] = (uint8_t)(st.size() - 1);
+            if (cl > 0 && reach < cl && st.size() < 255) st.push_back((uint16_t)cl);
+            reach = std::max(reach, cl);
+            const eidx c = c0 + cl;
+            if (c < n)
+            {
+                const eidx* b = Sy.idx.data() + Sy.ptr[c];
+                const eidx* e = Sy.idx.data() + Sy.ptr[c + 1];
+                const eidx* it = std::lower_bound(b, e, r1);   // first row beyond the diagonal block
+                if (it > b) reach = std::max(reach, (int)(*(it - 1) - c0));
+            }
+            comp_of[(size_t)k * nb + cl] = (uint8_t)(st.size() - 1);
         }
     }
-    // 2. components that receive updates from earlier block columns: rows of the strictly-lower blocks of block row k
-    //    (the upper blocks of block column k mirror them)
+    // 2. components that receive updates from earlier block columns = components holding a row of a strictly-lower
+    //    block of their block row
     std::vector<std::vector<char>> ext(bl);
     for (eidx k = 0; k < bl; ++k) ext[k].assign(comp_start[k].size(), 0);
-    std::vector<std::vector<uint32_t>> lower_rowmask_comp;  // unused placeholder to keep the code simple
-    for (eidx J = 0; J < bl; ++J)
-        for (eptr g = B.bcol_ptr[J]; g < B.bcol_ptr[J + 1]; ++g)
-        {
-            const eidx I = B.bcol_row[g];
-            if (I <= J) continue;
-            const int64_t sl = B.slot_of_block[g];
-            if (sl < 0) continue;
-            const pangulu_storage_slot_t& b = B.slots[sl];
-            const iptr nnz = b.columnpointer[nb];
-            for (iptr e = 0; e < nnz; ++e) ext[I][comp_of[I][b.rowindex[e]]] = 1;
-        }
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t c = 0; c < (int64_t)n; ++c)
+    {
+        const eidx r1 = ((eidx)c / nb + 1) * nb;
+        const eidx* b = Sy.idx.data() + Sy.ptr[c];
+        const eidx* e = Sy.idx.data() + Sy.ptr[c + 1];
+        for (const eidx* it = std::lower_bound(b, e, r1); it < e; ++it) ext[*it / nb][comp_of[*it]] = 1;  // (benign race: all writers store 1)
+    }
     // 3. groups: runs of adjacent components with equal `ext`, at most DIAG_MAX_GROUPS
-    std::vector<std::vector<uint8_t>> group_of(bl);  // index -> group
+    std::vector<uint8_t> group_of((size_t)bl * nb, 0);  // index -> group of its diagonal block
     for (eidx k = 0; k < bl; ++k)
     {
         const std::vector<uint16_t>& st = comp_start[k];
@@ -102,30 +105,40 @@ void diag_groups(const BlockStore& B, Schedule& S)
             if (ext[k][c] != ext[k][c - 1] && ng < DIAG_MAX_GROUPS) bd[ng++] = st[c];
         for (int g = ng; g <= DIAG_MAX_GROUPS; ++g) bd[g] = (uint16_t)nb;
         S.group_count[k] = (uint8_t)ng;
-        group_of[k].assign((size_t)nb, 0);
         for (int g = 0; g < ng; ++g)
-            for (int c = bd[g]; c < bd[g + 1]; ++c) group_of[k][c] = (uint8_t)g;
+            for (int c = bd[g]; c < bd[g + 1]; ++c) group_of[(size_t)k * nb + c] = (uint8_t)g;
     }
     // 4. which groups a strictly-lower block (I,J) touches: by its columns (groups of J) and by its rows (groups of I);
     //    the upper block (J,I) has the transposed pattern
 #pragma omp parallel for schedule(dynamic, 8)
     for (int64_t J = 0; J < (int64_t)bl; ++J)
+    {
+        const eidx c0 = (eidx)J * nb, c1 = std::min<eidx>(n, c0 + nb);
+        for (eidx c = c0; c < c1; ++c)
+        {
+            const uint8_t gc = (uint8_t)(1u << group_of[c]);
+            const eidx* b = Sy.idx.data() + Sy.ptr[c];
+            const eidx* e = Sy.idx.data() + Sy.ptr[c + 1];
+            const eidx* it = std::lower_bound(b, e, c0 + (eidx)nb);
+            int64_t gid = -1;
+            eidx cur = (eidx)-1;
+            for (; it < e; ++it)
+            {
+                const eidx I = *it / nb;
+                if (I != cur) { cur = I; gid = B.find_block(I, (eidx)J); }
+                if (gid < 0) continue;
+                S.colgroups[gid] |= gc;
+                S.rowgroups[gid] |= (uint8_t)(1u << group_of[*it]);
+            }
+        }
+    }
+    for (eidx J = 0; J < bl; ++J)
         for (eptr g = B.bcol_ptr[J]; g < B.bcol_ptr[J + 1]; ++g)
         {
             const eidx I = B.bcol_row[g];
-            if (I <= (eidx)J) continue;
-            const int64_t sl = B.slot_of_block[g];
-            if (sl < 0) continue;
-            const pangulu_storage_slot_t& b = B.slots[sl];
-            uint8_t cg = 0, rg = 0;
-            for (int c = 0; c < nb; ++c)
-                if (b.columnpointer[c + 1] > b.columnpointer[c]) cg |= (uint8_t)(1u << group_of[J][c]);
-            const iptr nnz = b.columnpointer[nb];
-            for (iptr e = 0; e < nnz; ++e) rg |= (uint8_t)(1u << group_of[I][b.rowindex[e]]);
-            S.colgroups[g] = cg;
-            S.rowgroups[g] = rg;
-            const int64_t gu = B.find_block((eidx)J, I);  // upper block (J, I): rows in block J, columns in block I
-            if (gu >= 0) { S.rowgroups[gu] = cg; S.colgroups[gu] = rg; }
+            if (I <= J) continue;
+            const int64_t gu = B.find_block(J, I);  // upper block (J, I): rows in block J, columns in block I
+            if (gu >= 0) { S.rowgroups[gu] = S.colgroups[g]; S.colgroups[gu] = S.rowgroups[g]; }
         }
 }
 
@@ -133,7 +146,15 @@ void build_schedule(BlockStore& B, Schedule& S)
 {
     const eidx bl = B.block_length;
     const size_t nblk = B.bcol_ptr[bl];
-    diag_groups(B, S);
+    if (S.group_count.size() != bl)
+    {
+        // diag_groups() was not run: every diagonal block is one group
+        S.group_bounds.assign((size_t)bl * (DIAG_MAX_GROUPS + 1), (uint16_t)B.nb);
+        for (eidx k = 0; k < bl; ++k) S.group_bounds[(size_t)k * (DIAG_MAX_GROUPS + 1)] = 0;
+        S.group_count.assign(bl, 1);
+        S.colgroups.assign(nblk, 1);
+        S.rowgroups.assign(nblk, 1);
+    }
     constexpr int MG = DIAG_MAX_GROUPS;
     S.depth_offdiag.assign(nblk, 0);
     S.depth_diag.assign((size_t)bl * MG, 0);

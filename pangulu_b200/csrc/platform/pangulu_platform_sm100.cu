@@ -1665,6 +1665,14 @@ long long pangulu_sm100_plan_flag_offset(pangulu_sm100_plan* pl, const void* d_v
     if (it == pl->ids.end()) return -1;
     return (long long)((char*)(pl->mp.done + it->second) - (char*)pl->mega_buf);
 }
+long long pangulu_sm100_plan_flag_offset2(pangulu_sm100_plan* pl, const void* d_value, int group)
+{
+    return pangulu_sm100_plan_flag_offset(pl, (const char*)d_value + group);
+}
+void pangulu_sm100_plan_expect_remote2(pangulu_sm100_plan* pl, const void* d_value, int group)
+{
+    pangulu_sm100_plan_expect_remote(pl, (const char*)d_value + group);
+}
 void pangulu_sm100_plan_expect_remote(pangulu_sm100_plan* pl, const void* d_value)
 {
     auto it = pl->ids.find(d_value);
@@ -1680,6 +1688,8 @@ void pangulu_sm100_plan_add_push2(pangulu_sm100_plan* pl, const void* d_value_lo
     e.peer_dense = nullptr;
     e.src_dense = nullptr;
     e.dense_count = 0;
+    e.off = 0xffffffffu;
+    e.cnt = 0;
     if (peer_dense)
     {
         auto d = pl->dense_of_val.find(d_value_local);
@@ -1694,6 +1704,20 @@ void pangulu_sm100_plan_add_push2(pangulu_sm100_plan* pl, const void* d_value_lo
 void pangulu_sm100_plan_add_push(pangulu_sm100_plan* pl, const void* d_value_local, void* peer_value, void* peer_flag)
 {
     pangulu_sm100_plan_add_push2(pl, d_value_local, peer_value, peer_flag, nullptr);
+}
+// group `group` of a diagonal half: its entries [off, off+cnt) are copied when the group's GETRF task is done
+void pangulu_sm100_plan_add_push3(pangulu_sm100_plan* pl, const void* d_value_local, int group, unsigned int off, unsigned int cnt, void* peer_value,
+                                  void* peer_flag)
+{
+    auto it = pl->ids.find((const char*)d_value_local + group);
+    if (it == pl->ids.end()) return;
+    MegaPush<T> e;
+    memset(&e, 0, sizeof e);
+    e.peer_val = (T*)peer_value;
+    e.peer_flag = (int*)peer_flag;
+    e.off = off;
+    e.cnt = cnt;   // (may be 0: nothing to copy, the flag is still raised)
+    pl->h_push[it->second].push_back(e);
 }
 double pangulu_sm100_plan_stat(pangulu_sm100_plan* pl, const char* key)
 {

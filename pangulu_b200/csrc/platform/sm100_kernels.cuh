@@ -1150,7 +1150,8 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 // running CTA, so the spin waits cannot deadlock.
 // ================================================================================================
 struct MegaTask { int kind, a, b, c; };
-template <class T> struct MegaPush { T* peer_val; int* peer_flag; T* peer_dense; const T* src_dense; size_t dense_count; };
+// off/cnt: entry range of the value array to copy (off = 0xffffffff: the whole array, length given by the pushing task)
+template <class T> struct MegaPush { T* peer_val; int* peer_flag; T* peer_dense; const T* src_dense; size_t dense_count; u32 off, cnt; };
 enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6, MEGA_CPANEL = 7 };
 
 template <class T>
@@ -1226,7 +1227,9 @@ __device__ __forceinline__ void push_block(const int* push_ptr, const MegaPush<T
     for (int e = e0; e < e1; ++e)
     {
         T* dst = pushes[e].peer_val;
-        for (u32 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+        const bool whole = pushes[e].off == 0xffffffffu;
+        const u32 o = whole ? 0u : pushes[e].off, cnt = whole ? n : pushes[e].cnt;
+        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[o + i] = src[o + i];
         if (pushes[e].peer_dense)
         {
             // the consumer reads the block through its compact dense copy: same layout on both ranks

@@ -122,9 +122,9 @@ class PanguLU:
 
     # -- multi-GPU wiring ---------------------------------------------------------------------------------
     def mirror_table(self) -> np.ndarray:
-        """int64[n, 6]: remote blocks this rank reads (brow, bcol, kind, value offset, flag offset, dense-copy offset)."""
+        """int64[n, 7]: remote blocks this rank reads (brow, bcol, kind, value offset, flag offset, dense-copy offset, group)."""
         n = int(self.L.pangulu_sm100_driver_mirror_table(self._h, None, 0))
-        out = np.zeros((max(n, 1), 6), dtype=np.int64)
+        out = np.zeros((max(n, 1), 7), dtype=np.int64)
         self.L.pangulu_sm100_driver_mirror_table(self._h, out.ctypes.data, n)
         return out[:n]
 

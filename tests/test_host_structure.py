@@ -117,25 +117,28 @@ def C_addr(ptr):
     return ctypes.addressof(ptr.contents)
 
 
+@pytest.mark.parametrize("split", [0, 1], ids=["whole-diagonals", "diagonal-groups"])
 @pytest.mark.parametrize("nproc", [2, 4, 8])
-def test_block_cyclic_ownership_partitions_the_tasks(nproc):
+def test_block_cyclic_ownership_partitions_the_tasks(nproc, split):
     """2D block-cyclic owner-computes (src/pangulu_common.h:135, src/pangulu.c:83-90): the ranks' task lists are a
-    partition of the single-rank list, and every operand a rank reads is a block it holds."""
+    partition of the single-rank list (GETRF tasks per independent group when the diagonal blocks are split: every rank
+    derives the same groups from the symbolic pattern), and every operand a rank reads is a block it holds."""
     A = matrices.poisson3d(10)
     nb = 32
-    base = PanguLU(A, nb=nb, host_only=True, split_diag=0)
+    key = lambda t: (int(t["row"]), int(t["col"]), int(t["kernel_id"]), int(t["task_level"]), int(t["compare_flag"]) >> 32)
+    base = PanguLU(A, nb=nb, host_only=True, split_diag=split)
     t0, _ = base.schedule()
-    all_tasks = sorted((int(t["row"]), int(t["col"]), int(t["kernel_id"]), int(t["task_level"])) for t in t0)
+    all_tasks = sorted(key(t) for t in t0)
     base.finalize()
     got = []
     pq = {2: (1, 2), 4: (2, 2), 8: (2, 4)}[nproc]
     for r in range(nproc):
-        s = PanguLU(A, nb=nb, host_only=True, rank=r, nproc=nproc)
+        s = PanguLU(A, nb=nb, host_only=True, rank=r, nproc=nproc, split_diag=split)
         assert (int(s.info("p")), int(s.info("q"))) == pq
         t, _ = s.schedule()
         for x in t:
             assert (int(x["row"]) % pq[0]) * pq[1] + int(x["col"]) % pq[1] == r
-        got += [(int(x["row"]), int(x["col"]), int(x["kernel_id"]), int(x["task_level"])) for x in t]
+        got += [key(x) for x in t]
         s.finalize()
     assert sorted(got) == all_tasks
 

@@ -23,7 +23,7 @@ WORKER = textwrap.dedent("""
     made = s.connect()
     p, q = int(s.info("p")), int(s.info("q"))
     # every mirrored block belongs to another rank of my process row (L) / process column (U) / both (diagonal halves)
-    for brow, bcol, kind, voff, foff, doff in table:
+    for brow, bcol, kind, voff, foff, doff, grp in table:
         owner = (brow %% p) * q + (bcol %% q)
         assert owner != rank
         if kind == 0 and brow > bcol: assert brow %% p == rank // q
