@@ -38,7 +38,7 @@ NOMINAL_FP64_TFLOPS = 40.0  # B200 FP64 / FP64-tensor nominal peak
 # MEASURED_PEAKS.json carries HBM and bf16 numbers only; the FP64 tensor (DMMA.8x8x4) peak was measured on this pool with
 # scripts/micro/dmma_bench.cu (profiles/r01_dmma_microbench.txt): 37.0 TFLOP/s at 1965 MHz, 16.1 cycles per DMMA per SM sub-partition
 MEASURED_DMMA_TFLOPS = 37.0
-TASK_KINDS = ["ssssm_tile", "ssssm_sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel_sparse", "ssssm_compact", "panel_compact"]
+TASK_KINDS = ["ssssm_tile", "ssssm_sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel_sparse", "ssssm_compact", "panel_compact", "diag_densify"]
 
 
 def parse_args():

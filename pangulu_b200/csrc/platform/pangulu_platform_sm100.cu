@@ -7,6 +7,7 @@
 // (src/platforms/02_NONSHAREDMEM/01_GPU/000_CUDA/pangulu_platform_0201000.cu:31-50).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -220,6 +221,7 @@ struct Program
     std::vector<CPanelTask> cptasks;  // (panel task, dense diagonal, first compact row/column) slices of the compact panel solves
     std::vector<int> getrf_dd;        // per GETRF task: dense triangular copies to refresh (index) or -1
     std::vector<const pangulu_storage_slot_t*> getrf_slot;  // lower-half slot of each GETRF task
+    std::vector<const pangulu_storage_slot_t*> panel_diag_slot;  // lower-half slot of the diagonal block of each panel task
     std::vector<Step> steps;
     std::vector<Download> downloads;  // referenced by steps of kind -1 (off/count)
 };
@@ -642,6 +644,7 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 }
                 P.panel.push_back(Q);
                 P.panel_slot.push_back(t.opdst);
+                P.panel_diag_slot.push_back(lo);
                 st.count++;
                 if (eager_download)
                 {
@@ -954,6 +957,11 @@ struct pangulu_sm100_plan
     std::vector<const void*> op_val;  // per compact copy: device value array of the block it mirrors (sync id key)
     void* diag_dense_buf = nullptr;   // dense triangular copies of diagonal blocks (compact panel path)
     std::unordered_map<const void*, size_t> dense_of_val;  // device value array -> compact copy index
+    // dense triangular copies of REMOTE diagonal blocks: refreshed on this rank by a task that waits for the mirrored
+    // halves (one per independent group)
+    struct DDens { int getrf_index, dd, group; bool need_u, need_lt; const pangulu_storage_slot_t* lower; };
+    std::vector<DDens> ddens;
+    std::unordered_map<const pangulu_storage_slot_t*, std::array<int, 4>> ddens_of;  // lower slot -> ddens index per group
     double stat_ct_pairtiles = 0, stat_ct_chunks = 0, stat_ct_dmma = 0, stat_ct_abytes = 0, stat_ct_tasks = 0, stat_ct_msum = 0, stat_ct_ntsum = 0;
     size_t dense_total_bytes = 0;
     // persistent executor
@@ -1081,6 +1089,34 @@ void build_mega(pangulu_sm100_plan* pl)
                 for (int gr = 0; gr < 4; ++gr)
                     if ((gm >> gr) & 1u) { dp[ndp] = id_of(gkey(P.panel[ti].diag.val, gr)); touch(dp[ndp]); ++ndp; }
                 if (ndp == 0) { dp[0] = id_of(P.panel[ti].diag.val); touch(dp[0]); }
+                if (st.kind == K_CPANEL && !P.panel_diag_slot.empty())
+                {
+                    // the diagonal block lives on another rank: depend on the local refresh of its dense triangular copies
+                    auto rd = pl->ddens_of.find(P.panel_diag_slot[ti]);
+                    if (rd != pl->ddens_of.end())
+                    {
+                        ndp = 0;
+                        dp[0] = dp[1] = dp[2] = dp[3] = -1;
+                        for (int gr = 0; gr < 4; ++gr)
+                        {
+                            if (!((gm >> gr) & 1u) || rd->second[gr] < 0) continue;
+                            pangulu_sm100_plan::DDens& de = pl->ddens[rd->second[gr]];
+                            const int ready = id_of((const char*)&de);
+                            touch(ready);
+                            if (!produced[ready])
+                            {
+                                produced[ready] = 1;
+                                const GetrfTask<T>& Gd = P.getrf[de.getrf_index];
+                                const int wl = de.need_lt ? id_of(gkey(Gd.lower.val, gr)) : -1, wu = de.need_u ? id_of(gkey(Gd.upper.val, gr)) : -1;
+                                if (wl >= 0) touch(wl);
+                                if (wu >= 0) touch(wu);
+                                getrf_id[de.getrf_index] = make_int2(wl, wu);
+                                tasks.push_back({MEGA_DDENS, de.getrf_index, ready, 0});
+                            }
+                            dp[ndp++] = ready;
+                        }
+                    }
+                }
                 panel_dep[ti] = make_int4(dp[0], dp[1], dp[2], dp[3]);
                 panel_id[ti] = make_int2(ib, dp[0]);
                 produced[ib] = 1;
@@ -1440,26 +1476,23 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     P.getrf_dd.assign(P.getrf.size(), -1);
     if (!ops.empty() && g.opt.cpanel != 0 && sizeof(T) <= 8 && nb % 16 == 0 && nb <= 256)
     {
-        struct DiagNeed { bool u = false, lt = false; int index = -1; };
+        struct DiagNeed { bool u = false, lt = false; int index = -1; bool remote = false; };
         std::unordered_map<const pangulu_storage_slot_t*, DiagNeed> need;  // keyed by the lower-half slot
         std::vector<const pangulu_storage_slot_t*> diag_of(P.panel.size(), nullptr);
         std::vector<char> compact(P.panel.size(), 0);
-        // the diagonal halves of a panel task were resolved when the task was appended; find the lower-half slot again
-        // through the value pointer of the task's diagonal operand
-        std::unordered_map<const void*, const pangulu_storage_slot_t*> lower_of_val;
-        for (const pangulu_storage_slot_t* lo : P.getrf_slot)
-        {
-            lower_of_val.emplace(lo->d_value, lo);
-            lower_of_val.emplace(lo->related_block->d_value, lo);
-        }
+        std::vector<const pangulu_storage_slot_t*> remote_order;
         for (size_t i = 0; i < P.panel.size(); ++i)
         {
             if (P.panel[i].dense < 0) continue;
-            auto it = lower_of_val.find(P.panel[i].diag.val);
-            if (it == lower_of_val.end()) continue;  // diagonal block factored by another rank
+            const pangulu_storage_slot_t* lo = P.panel_diag_slot[i];
+            const bool remote = lo->bin_id != 0;   // diagonal block factored by another rank: its halves arrive in mirror slots
+            if (remote && g.opt.executor != 1) continue;
             compact[i] = 1;
-            diag_of[i] = it->second;
-            DiagNeed& dn = need[it->second];
+            diag_of[i] = lo;
+            const bool fresh = need.find(lo) == need.end();
+            DiagNeed& dn = need[lo];
+            dn.remote = remote;
+            if (remote && fresh) remote_order.push_back(lo);
             if ((P.panel[i].kind & 0xff) == PANGULU_TASK_GESSM) dn.lt = true; else dn.u = true;
         }
         const size_t tri = (size_t)(nb / 16) * nb * PSM_CT_BLD;  // values per triangular copy
@@ -1493,6 +1526,51 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             else dd.lt = (T*)nullptr - 1;
             dds.push_back(dd);
         }
+        // remote diagonal blocks: same copies, refreshed by MEGA_DDENS tasks (one pseudo GETRF descriptor per group)
+        for (const pangulu_storage_slot_t* lo : remote_order)
+        {
+            DiagNeed& dn = need[lo];
+            const pangulu_storage_slot_t* up = lo->related_block;
+            dn.index = (int)dds.size();
+            DiagDense<T> dd;
+            memset(&dd, 0, sizeof dd);
+            if (dn.u)
+            {
+                dd.u = (T*)nullptr + total;
+                total += tri;
+                for (int r = 0; r < nb; ++r)
+                    for (u32 e = r ? up->columnpointer[r] : 0u; e < up->columnpointer[r + 1]; ++e) dd.umask[r / 16] |= 1u << (up->rowindex[e] / 16);
+            }
+            else dd.u = (T*)nullptr - 1;
+            if (dn.lt)
+            {
+                dd.lt = (T*)nullptr + total;
+                total += tri;
+                for (int k = 0; k < nb; ++k)
+                    for (u32 e = k ? lo->columnpointer[k] : 0u; e < lo->columnpointer[k + 1]; ++e) dd.ltmask[k / 16] |= 1u << (lo->rowindex[e] / 16);
+            }
+            else dd.lt = (T*)nullptr - 1;
+            dds.push_back(dd);
+            const DiagGroupInfo* gi = groups_of(lo);
+            const int ng = gi ? gi->ng : 1;
+            std::array<int, 4> per_group = {-1, -1, -1, -1};
+            for (int gr = 0; gr < ng; ++gr)
+            {
+                GetrfTask<T> G;
+                G.lower = blk_csc(lo);
+                G.upper = blk_upper_diag(up);
+                G.c0 = gi ? gi->bounds[gr] : 0;
+                G.c1 = gi ? gi->bounds[gr + 1] : nb;
+                G.grp = gr;
+                G.pad = 0;
+                per_group[gr] = (int)pl->ddens.size();
+                pl->ddens.push_back({(int)P.getrf.size(), dn.index, gr, dn.u, dn.lt, lo});
+                P.getrf.push_back(G);
+                P.getrf_slot.push_back(lo);
+                P.getrf_dd.push_back(dn.index);
+            }
+            pl->ddens_of.emplace(lo, per_group);
+        }
         if (!dds.empty())
         {
             CK(cudaMalloc(&pl->diag_dense_buf, total * sizeof(T) + 256));
@@ -1514,12 +1592,13 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             const size_t nplain = order.size();
             for (size_t i = st.off; i < st.off + st.count; ++i) if (compact[i]) order.push_back(i);
             std::vector<PanelTask<T>> tp;
-            std::vector<const pangulu_storage_slot_t*> ts, td;
+            std::vector<const pangulu_storage_slot_t*> ts, td, tds;
             std::vector<char> tc;
-            for (size_t i : order) { tp.push_back(P.panel[i]); ts.push_back(P.panel_slot[i]); td.push_back(diag_of[i]); tc.push_back(compact[i]); }
+            for (size_t i : order) { tp.push_back(P.panel[i]); ts.push_back(P.panel_slot[i]); td.push_back(diag_of[i]); tc.push_back(compact[i]); tds.push_back(P.panel_diag_slot[i]); }
             for (size_t k = 0; k < order.size(); ++k)
             {
                 P.panel[st.off + k] = tp[k]; P.panel_slot[st.off + k] = ts[k]; diag_of[st.off + k] = td[k]; compact[st.off + k] = tc[k];
+                P.panel_diag_slot[st.off + k] = tds[k];
             }
             cs.off = st.off + nplain;
             cs.count = st.count - nplain;
@@ -1599,6 +1678,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
     std::vector<CTileTask>().swap(P.ctasks);
     std::vector<CPanelTask>().swap(P.cptasks);
     std::vector<const pangulu_storage_slot_t*>().swap(P.getrf_slot);
+    std::vector<const pangulu_storage_slot_t*>().swap(P.panel_diag_slot);
     std::vector<u16>().swap(pl->reg.meta);
     std::vector<const pangulu_storage_slot_t*>().swap(P.panel_slot);
     return pl;

@@ -1152,7 +1152,7 @@ ssssm_tile2_kernel(int nb, const SsssmDest<T>* __restrict__ dests, const SsssmPa
 struct MegaTask { int kind, a, b, c; };
 // off/cnt: entry range of the value array to copy (off = 0xffffffff: the whole array, length given by the pushing task)
 template <class T> struct MegaPush { T* peer_val; int* peer_flag; T* peer_dense; const T* src_dense; size_t dense_count; u32 off, cnt; };
-enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6, MEGA_CPANEL = 7 };
+enum { MEGA_TILE = 0, MEGA_SPARSE = 1, MEGA_GETRF_SMEM = 2, MEGA_GETRF_DENSE = 3, MEGA_GETRF_GLOBAL = 4, MEGA_PANEL = 5, MEGA_CTILE = 6, MEGA_CPANEL = 7, MEGA_DDENS = 8 };
 
 template <class T>
 struct MegaParams
@@ -1362,6 +1362,25 @@ mega_kernel(const MegaParams<T> P)
             // push, after which the flag may be raised)
             if (id.x != id.y) push_block<T>(P.push_ptr, P.pushes, id.x, G.lower.val, G.lower.ptr[nb]);
             push_block<T>(P.push_ptr, P.pushes, id.y, G.upper.val, G.upper.ptr[nb]);
+            break;
+        }
+        case MEGA_DDENS:
+        {
+            // refresh the dense triangular copies of a diagonal block factored by ANOTHER rank, once its mirrored halves
+            // (one independent group of them) have arrived; mt.b = sync id the compact panel solves wait for
+            const GetrfTask<T> G = P.getrf[mt.a];
+            const int2 id = P.getrf_id[mt.a];
+            if (tid == 0)
+            {
+                if (id.x >= 0) spin_until_set(P.done + id.x, P.multi);
+                if (id.y >= 0) spin_until_set(P.done + id.y, P.multi);
+            }
+            __syncthreads();
+            if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            diag_densify<T>(nb, G, P.dds[P.getrf_dd[mt.a]]);
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(P.done + mt.b, 1);
             break;
         }
         case MEGA_CPANEL:

@@ -24,9 +24,9 @@ if a.out:
     np.save(a.out, buf)
 kind = (buf[:, 0] & 0xff).astype(int); npairs = (buf[:, 0] >> 8).astype(int); t0 = buf[:, 1].min()
 fetch, start, end = [(buf[:, i] - t0).astype(np.int64) / 1e3 for i in (1, 2, 3)]
-names = ["tile", "sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel", "ctile", "cpanel"]
+names = ["tile", "sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel", "ctile", "cpanel", "ddens"]
 print(f"gstrf {t*1e3:.1f} ms, {n} tasks, span {end.max()/1e3:.1f} ms")
-for k in range(8):
+for k in range(9):
     m = kind == k
     if m.any():
         run, wait = end[m] - start[m], start[m] - fetch[m]
