@@ -57,7 +57,7 @@ void pangulu_finalize(void **pangulu_handle);
  *                     2 host buffers + resident plan (upload values, run the plan, download factors)
  *   "schedule"        wave of an SSSSM update: 0 lazy (the wave that finalises its destination), 1 eager (first wave
  *                     after both operands are final), 2 (default) windowed: max(eager, destination's wave - "lookahead")
- *   "lookahead"       window of policy 2 in waves (default 6)
+ *   "lookahead"       window of policy 2 in waves (default 2)
  *   "verbose"         1 prints the reference's info lines
  *   "host_only"       1 builds ordering/symbolic/blocks/schedule in host memory only (CPU-side tests of the
  *                     host logic); pangulu_gstrf on such a handle is a fatal error -- there is no CPU path

@@ -36,7 +36,7 @@ struct DriverConfig
     long long verbose = 0;
     long long host_only = 0;
     long long schedule = 2;
-    long long lookahead = 6;
+    long long lookahead = 2;
     long long split_diag = 1;  // schedule independent groups of diagonal blocks separately (single rank)
 };
 DriverConfig g_cfg;

@@ -130,7 +130,7 @@ struct Schedule
     std::vector<uint8_t> rowgroups;     //                                       groups of diagonal block I its rows touch
     uint64_t n_getrf = 0, n_tstrf = 0, n_gessm = 0, n_ssssm = 0;
     int policy = 2;                     // 0 lazy (updates in the destination's wave), 1 eager (as soon as operands are final), 2 windowed
-    int lookahead = 6;                  // policy 2: waves before the destination's finalisation at which slack updates run
+    int lookahead = 2;                  // policy 2: waves before the destination's finalisation at which slack updates run
 };
 // independent groups of the diagonal blocks, from the element-level symbolic pattern (call before build_schedule)
 void diag_groups(const BlockStore& B, const Symbolic& Sy, Schedule& S);

@@ -52,7 +52,7 @@ def driver_config(vtype: str = "r64", **kw) -> None:
 
 class PanguLU:
     def __init__(self, A, nb: int = 256, *, ordering: int = -1, mode: int = 0, rank: int = 0, nproc: int = 1,
-                 host_only: bool = False, nthread: int = 1, verbose: bool = False, schedule: int = 2, lookahead: int = 6,
+                 host_only: bool = False, nthread: int = 1, verbose: bool = False, schedule: int = 2, lookahead: int = 2,
                  split_diag: int = 1):
         """A: scipy.sparse matrix (any format; converted to sorted CSC) of dtype f64/f32/c128/c64."""
         import scipy.sparse as sp

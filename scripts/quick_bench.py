@@ -8,7 +8,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--case", default="p3"); ap.add_argument("--size", type=int, default=32)
 ap.add_argument("--nb", type=int, default=128); ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--mode", type=int, default=1); ap.add_argument("--profile", type=int, default=1)
-ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--schedule", type=int, default=2); ap.add_argument("--lookahead", type=int, default=6)
+ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--schedule", type=int, default=2); ap.add_argument("--lookahead", type=int, default=2)
 a = ap.parse_args()
 A = {"p3": matrices.poisson3d, "p2": matrices.laplace2d, "s27": matrices.stencil27}[a.case](a.size)
 from pangulu_b200 import _lib

@@ -5,7 +5,7 @@ import numpy as np
 from pangulu_b200 import PanguLU, matrices, _lib
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=48); ap.add_argument("--nb", type=int, default=256)
-ap.add_argument("--schedule", type=int, default=2); ap.add_argument("--lookahead", type=int, default=6)
+ap.add_argument("--schedule", type=int, default=2); ap.add_argument("--lookahead", type=int, default=2)
 ap.add_argument("--opt", action="append", default=[]); ap.add_argument("--out", default="")
 a = ap.parse_args()
 L = _lib.load("r64")

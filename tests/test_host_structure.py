@@ -72,7 +72,7 @@ def test_schedule_respects_dependencies(policy):
     update of a destination runs after the wave that finalises it (lazy policy: exactly in that wave)."""
     A = matrices.poisson3d(12)
     nb = 32
-    s = PanguLU(A, nb=nb, host_only=True, schedule=policy, split_diag=0)
+    s = PanguLU(A, nb=nb, host_only=True, schedule=policy, split_diag=0, lookahead=6)
     try:
         tasks, wave_ptr = s.schedule()
         wave_of_task = np.repeat(np.arange(len(wave_ptr) - 1), np.diff(wave_ptr.astype(np.int64)))
