@@ -15,6 +15,7 @@ import os
 import subprocess
 import sys
 import tempfile
+import time
 
 import numpy as np
 
@@ -98,33 +99,64 @@ def main(argv=None):
     np.savez(a.out, **out)
 
 
-def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthread=1, quiet=True, flavour="cpu"):
-    """Factor scipy CSC matrix A with the reference in a subprocess; returns the loaded npz dict."""
+def run_reference(A, nb, vtype="r64", perf=False, solve=True, blocks=True, nthread=1, quiet=True, flavour="cpu", ranks=1):
+    """Factor scipy CSC matrix A with the reference in a subprocess; returns the loaded npz dict (of rank 0).
+
+    ranks > 1: that many reference processes ("MPI ranks" of the shim oracle/shims/mpi_local.c: messages travel through
+    POSIX shared memory) factor the matrix together, as `mpirun -np ranks` would; `t_gstrf` is then the maximum over the
+    ranks.  Only the timing is meaningful in that mode (every rank holds its own blocks)."""
     import scipy.sparse as sp
 
     A = sp.csc_matrix(A)
     A.sort_indices()
     with tempfile.TemporaryDirectory() as td:
-        inp, out = os.path.join(td, "in.npz"), os.path.join(td, "out.npz")
+        inp = os.path.join(td, "in.npz")
         np.savez(inp, indptr=A.indptr.astype(np.uint64), indices=A.indices.astype(np.uint32), data=A.data, n=A.shape[0])
-        cmd = [sys.executable, "-m", "oracle.ref_run", inp, out, "--nb", str(nb), "--vtype", vtype, "--nthread", str(nthread),
-               "--flavour", flavour]
-        if perf:
-            cmd.append("--perf")
-        if not solve:
-            cmd.append("--no-solve")
-        if not blocks:
-            cmd.append("--no-blocks")
         # The reference leaves the value arrays of some fill-in entries uninitialised (malloc without memset in its
         # block construction); on small problems recycled heap memory then shows up as garbage, even NaN, in the
         # factors.  glibc's MALLOC_PERTURB_=255 makes malloc hand out zero-filled memory (byte ^ 0xff), which is what
         # the algorithm assumes -- the reference sources stay untouched.
         env = dict(os.environ, MALLOC_PERTURB_="255")
-        r = subprocess.run(cmd, cwd=_ROOT, env=env, stdout=subprocess.PIPE if quiet else None, stderr=subprocess.STDOUT if quiet else None)
-        if r.returncode != 0:
-            raise RuntimeError("reference run failed:\n" + (r.stdout.decode(errors="replace") if r.stdout else ""))
-        with np.load(out, allow_pickle=False) as z:
-            return {k: z[k] for k in z.files}
+        if ranks > 1:
+            from oracle.ref import ref_lib_path
+
+            session = "pgl_%d_%d" % (os.getpid(), int(time.time() * 1e3) % 1000000)
+            mk = ("import ctypes,sys; sys.exit(ctypes.CDLL(%r).pangulu_shim_create_session(%r, %d))"
+                  % (ref_lib_path(vtype, perf, flavour), session.encode(), ranks))
+            if subprocess.run([sys.executable, "-c", mk], cwd=_ROOT).returncode != 0:
+                raise RuntimeError("could not create the shared-memory session of the MPI shim")
+            env.update(PANGULU_SHIM_NP=str(ranks), PANGULU_SHIM_SESSION=session, OMP_NUM_THREADS="1")
+        procs, outs = [], []
+        for r in range(ranks):
+            out = os.path.join(td, f"out{r}.npz")
+            outs.append(out)
+            cmd = [sys.executable, "-m", "oracle.ref_run", inp, out, "--nb", str(nb), "--vtype", vtype, "--nthread", str(nthread),
+                   "--flavour", flavour]
+            if perf:
+                cmd.append("--perf")
+            if not solve or ranks > 1:
+                cmd.append("--no-solve")
+            if not blocks or ranks > 1:
+                cmd.append("--no-blocks")
+            e = dict(env, PANGULU_SHIM_RANK=str(r)) if ranks > 1 else env
+            procs.append(subprocess.Popen(cmd, cwd=_ROOT, env=e, stdout=subprocess.PIPE if quiet else None, stderr=subprocess.STDOUT if quiet else None))
+        for p in procs:
+            so = p.communicate()[0]
+            if p.returncode != 0:
+                for q in procs:
+                    if q.poll() is None:
+                        q.kill()
+                raise RuntimeError("reference run failed:\n" + (so.decode(errors="replace") if so else ""))
+        res = None
+        tmax = 0.0
+        for out in outs:
+            with np.load(out, allow_pickle=False) as z:
+                d = {k: z[k] for k in z.files}
+            tmax = max(tmax, float(d["t_gstrf"]))
+            if res is None:
+                res = d
+        res["t_gstrf"] = np.float64(tmax)
+        return res
 
 
 if __name__ == "__main__":
