@@ -427,7 +427,10 @@ def run_ours(a):
             "parity": {"factor_check_resident": check, "factor_check_e2e": check_e2e}}
     s.finalize()
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
