@@ -44,7 +44,7 @@ WORKER = textwrap.dedent("""
 """) % ROOT
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_mirror_tables_and_pushes_over_gloo(world, tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
