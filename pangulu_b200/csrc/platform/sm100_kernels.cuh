@@ -1294,10 +1294,12 @@ mega_kernel(const MegaParams<T> P)
         case MEGA_CTILE:
         {
             const SsssmDest<T> D = P.dests[mt.a];
-            if (tid == 0)
+            if (warp == 0)
             {
+                // operand blocks final?  One pair per lane: the acquire loads of a destination's pairs overlap instead of
+                // forming one chain (the block barrier below carries their ordering to the other warps)
                 const int2* deps = mt.kind == MEGA_CTILE ? P.cpair_dep : P.pair_dep;
-                for (u32 p = D.pair_begin; p < D.pair_end; ++p)
+                for (u32 p = D.pair_begin + (tid % PSM_WARP); p < D.pair_end; p += PSM_WARP)
                 {
                     const int2 dep = deps[p];
                     spin_until_set(P.done + dep.x, P.multi);
