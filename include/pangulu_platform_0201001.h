@@ -107,6 +107,9 @@ void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t *s, calculate_ty
  *   "getrf_mode"      0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense-promoted (nb <= 256)
  *   "executor"        plans only: 1 (default) persistent megakernel -- one launch per factorisation, device-side
  *                     dependency flags; 0 one launch per kernel class per wave
+ *   "spin_timeout_ms" persistent executor: a dependency wait longer than this (default 30000) ends the run with
+ *                     "[PanguLU ERROR] ..." and exit, the reference's error convention (…0201000.cu:31-50), instead of
+ *                     hanging the GPU (dead peer rank, CTAs not co-resident)
  *   "split_pairs", "tile_variant", "profile", "trace"   tuning / instrumentation, see DESIGN.md
  * returns 0, or -1 for an unknown key. */
 int pangulu_sm100_set_option(const char *key, long long value);
@@ -138,6 +141,8 @@ void pangulu_sm100_plan_destroy(pangulu_sm100_plan *plan);
 /* persistent executor with option "trace" = 1 at plan creation: per task {kind, fetch_ns, start_ns, end_ns}
  * (4 u64 per task) of the last execution; returns the number of tasks (call with out = NULL to size the buffer) */
 long long pangulu_sm100_plan_trace(pangulu_sm100_plan *plan, unsigned long long *out, long long cap);
+/* per task, in the order of plan_trace: FP64 tensor (DMMA.8x8x4) instructions the task issues (compact tile tasks, else 0) */
+long long pangulu_sm100_plan_task_work(pangulu_sm100_plan *plan, float *out, long long cap);
 
 /* Multi-GPU wiring of a persistent plan (one rank per GPU).  A block finalised by its owner is written by the
  * producing kernel itself into the mirror copy every consumer rank keeps (peer-mapped pointers over NVLink /
@@ -176,6 +181,7 @@ void pangulu_sm100_plan_launch(pangulu_sm100_plan *plan);
 /* CUDA IPC: 64-byte handle of a device allocation of this module / map a peer's allocation into this process */
 int pangulu_sm100_ipc_export(void *devptr, void *handle64);
 int pangulu_sm100_ipc_open(const void *handle64, void **devptr);
+int pangulu_sm100_ipc_close(void *devptr);
 
 /* Instrumentation (bench.py): kernels launched / device time per kernel class since the last reset.
  * cls: 0 getrf, 1 tstrf, 2 gessm, 3 ssssm-sparse, 4 ssssm-tile, 5 copy/aux.  Timing is off unless

@@ -90,6 +90,8 @@ void pangulu_sm100_driver_ipc_handles(void *handle, unsigned char *out192);
 long long pangulu_sm100_driver_mirror_table(void *handle, long long *out, long long cap);
 long long pangulu_sm100_driver_connect_peer(void *handle, const unsigned char *handles192, const long long *table, long long n);
 void pangulu_sm100_driver_commit(void *handle);
+/* close the peer mappings of an earlier round of connect_peer calls (reconnect after rebuild_plan; finalize does it too) */
+void pangulu_sm100_driver_disconnect(void *handle);
 void pangulu_sm100_driver_gstrf_reset(void *handle);
 void pangulu_sm100_driver_gstrf_launch(void *handle);
 /* independent groups of diagonal block k: bounds[0..ng] of the index ranges, returns ng (1 = not split) */
@@ -98,10 +100,22 @@ int pangulu_sm100_driver_diag_groups(void *handle, long long k, unsigned short *
 void pangulu_sm100_driver_rebuild_plan(void *handle);
 /* task trace of the last resident gstrf (see pangulu_sm100_plan_trace) */
 long long pangulu_sm100_driver_trace(void *handle, unsigned long long *out, long long cap);
+/* per traced task: DMMA instructions it issues (see pangulu_sm100_plan_task_work) */
+long long pangulu_sm100_driver_task_work(void *handle, float *out, long long cap);
 /* device -> host copy of the owned factors (resident mode) */
 void pangulu_sm100_driver_download(void *handle);
 /* the reference's gstrf self-check ||L(U1) - A1|| / ||A1|| (src/pangulu_numeric.c:1082-1341) on host factors */
 double pangulu_sm100_driver_factor_check(void *handle);
+/* The same check with the factors spread over several ranks, in the three passes the reference makes
+ * (src/pangulu_numeric.c:1082-1341: every rank multiplies the blocks it owns, the partial vectors are summed over the
+ * ranks).  All vectors have block_length*nb doubles (real part for the complex types):
+ *   check_ux  : ux  += U_owned * 1                     -> sum over ranks
+ *   check_lux : lux += L_owned * ux (+ ux on rank 0: the unit diagonal)  -> sum over ranks
+ *   check_ax  : ax = A_reordered * 1 (every rank holds A), returns n
+ * residual = ||lux - ax||_2 / ||ax||_2 over the first n entries. */
+void pangulu_sm100_driver_check_ux(void *handle, double *ux);
+void pangulu_sm100_driver_check_lux(void *handle, const double *ux, double *lux);
+long long pangulu_sm100_driver_check_ax(void *handle, double *ax);
 
 #ifdef __cplusplus
 }

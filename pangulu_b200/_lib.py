@@ -35,6 +35,7 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_ipc_export", "pangulu_sm100_ipc_open", "pangulu_sm100_plan_dense_base", "pangulu_sm100_plan_dense_offset",
     "pangulu_sm100_plan_add_push2", "pangulu_sm100_set_diag_groups", "pangulu_sm100_plan_stat",
     "pangulu_sm100_plan_flag_offset2", "pangulu_sm100_plan_expect_remote2", "pangulu_sm100_plan_add_push3",
+    "pangulu_sm100_ipc_close", "pangulu_sm100_plan_task_work",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [
@@ -45,7 +46,8 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_trace", "pangulu_sm100_driver_set_barrier", "pangulu_sm100_driver_ipc_handles",
     "pangulu_sm100_driver_mirror_table", "pangulu_sm100_driver_connect_peer", "pangulu_sm100_driver_commit",
     "pangulu_sm100_driver_gstrf_reset", "pangulu_sm100_driver_gstrf_launch", "pangulu_sm100_driver_set_mode",
-    "pangulu_sm100_driver_rebuild_plan", "pangulu_sm100_driver_diag_groups",
+    "pangulu_sm100_driver_rebuild_plan", "pangulu_sm100_driver_diag_groups", "pangulu_sm100_driver_disconnect", "pangulu_sm100_driver_task_work",
+    "pangulu_sm100_driver_check_ux", "pangulu_sm100_driver_check_lux", "pangulu_sm100_driver_check_ax",
 ]
 
 
@@ -180,6 +182,15 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_plan_trace.restype = C.c_longlong
     L.pangulu_sm100_driver_factor_check.argtypes = [vp]
     L.pangulu_sm100_driver_factor_check.restype = C.c_double
+    L.pangulu_sm100_plan_task_work.argtypes = [vp, vp, C.c_longlong]
+    L.pangulu_sm100_plan_task_work.restype = C.c_longlong
+    L.pangulu_sm100_driver_task_work.argtypes = [vp, vp, C.c_longlong]
+    L.pangulu_sm100_driver_task_work.restype = C.c_longlong
+    L.pangulu_sm100_driver_disconnect.argtypes = [vp]
+    L.pangulu_sm100_driver_check_ux.argtypes = [vp, vp]
+    L.pangulu_sm100_driver_check_lux.argtypes = [vp, vp, vp]
+    L.pangulu_sm100_driver_check_ax.argtypes = [vp, vp]
+    L.pangulu_sm100_driver_check_ax.restype = C.c_longlong
     L.platform = P
     _cache[vtype] = L
     return L

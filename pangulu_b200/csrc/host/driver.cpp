@@ -56,6 +56,11 @@ struct Handle
     int mode = 0;
     int rank = 0, nproc = 1;  // fixed at pangulu_init (later driver_config calls configure FUTURE handles only)
     bool factored = false;
+    // multi-GPU wiring: host barrier across the ranks, peer allocations mapped with CUDA IPC (closed in finalize /
+    // disconnect), and whether the current plan has been wired to the peers
+    void (*barrier)(void) = nullptr;
+    std::vector<void*> ipc_opened;
+    bool wired = false;
     std::map<std::string, double> times;
 };
 
@@ -211,17 +216,18 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
     {
         // one rank per GPU: the plan must have been wired to the peers (pangulu_sm100_driver_connect_peer/commit);
         // every rank clears its flags, all ranks meet, then the persistent kernels run and push blocks to each other
-        if (!g_barrier || !h->plan)
+        if (!h->barrier || !h->plan || !h->wired)
         {
-            fprintf(stderr, "[PanguLU ERROR] multi-rank gstrf needs a wired plan and a barrier (pangulu_sm100_driver_set_barrier)\n");
+            fprintf(stderr, "[PanguLU ERROR] multi-rank gstrf needs a plan wired to the peers (pangulu_sm100_driver_connect_peer + commit; again after "
+                            "rebuild_plan) and a host barrier (pangulu_sm100_driver_set_barrier)\n");
             exit(EXIT_FAILURE);
         }
         pangulu_sm100_plan_reset(h->plan);
         PSM(synchronize)();
-        g_barrier();
+        h->barrier();
         pangulu_sm100_plan_launch(h->plan);
         PSM(synchronize)();
-        g_barrier();
+        h->barrier();
     }
     else if (h->mode == 1)
     {
@@ -269,6 +275,15 @@ void pangulu_gstrs(sparse_value_t* rhs, pangulu_gstrs_options* gstrs_options, vo
     }
     Handle* h = (Handle*)*pangulu_handle;
     const eidx n = h->n;
+    if (h->nproc > 1)
+    {
+        // the triangular solves here walk the blocks of ONE rank; with the factors spread over several GPUs that would
+        // silently drop the remote blocks.  The reference's distributed gstrs (src/pangulu_sptrsv.c) is not part of
+        // this module's scope: refuse instead of returning a wrong x.
+        fprintf(stderr, "[PanguLU ERROR] pangulu_gstrs / pangulu_gssv on %d ranks: the sm_100a driver solves on one rank only; gather the factors "
+                        "(run gstrf with nproc = 1) or use PanguLU's own distributed gstrs\n", h->nproc);
+        exit(EXIT_FAILURE);
+    }
     const double t0 = wall_seconds();
     if (h->mode == 1)
     {
@@ -296,6 +311,9 @@ void pangulu_finalize(void** pangulu_handle)
     Handle* h = (Handle*)*pangulu_handle;
     if (!h) return;
     if (h->plan) pangulu_sm100_plan_destroy(h->plan);
+    for (void* p : h->ipc_opened) pangulu_sm100_ipc_close(p);
+    h->ipc_opened.clear();
+    if (g_barrier == h->barrier) g_barrier = nullptr;   // (the callback usually belongs to the object that owns this handle)
     if (!h->B.host_only)
         for (eidx k = 0; k < h->B.block_length; ++k)
             if (h->sched.group_count.size() > k && h->sched.group_count[k] > 1 && h->B.slot_of_diag[k] >= 0)
@@ -403,6 +421,16 @@ void pangulu_sm100_driver_rebuild_plan(void* handle)
     if (h->plan) pangulu_sm100_plan_destroy(h->plan);
     h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
                                         h->sched.tasks.data());
+    h->wired = false;   // several ranks: the new plan has new flags / compact copies; every rank must disconnect + connect again
+}
+
+// close the peer mappings of an earlier connect (before a new round of connect_peer calls, or before finalize)
+void pangulu_sm100_driver_disconnect(void* handle)
+{
+    Handle* h = (Handle*)handle;
+    for (void* p : h->ipc_opened) pangulu_sm100_ipc_close(p);
+    h->ipc_opened.clear();
+    h->wired = false;
 }
 
 void pangulu_sm100_driver_reset_values(void* handle, int also_device)
@@ -507,9 +535,15 @@ long long pangulu_sm100_driver_connect_peer(void* handle, const unsigned char* h
         ensure_plan(h);
         pangulu_sm100_ipc_open(handles128, (void**)&peer_buf);
         pangulu_sm100_ipc_open(handles128 + 64, (void**)&peer_sync);
+        h->ipc_opened.push_back(peer_buf);
+        h->ipc_opened.push_back(peer_sync);
         bool any_dense = false;
         for (long long i = 0; i < n; ++i) any_dense = any_dense || table[7 * i + 5] >= 0;
-        if (any_dense) pangulu_sm100_ipc_open(handles128 + 128, (void**)&peer_dense);
+        if (any_dense)
+        {
+            pangulu_sm100_ipc_open(handles128 + 128, (void**)&peer_dense);
+            h->ipc_opened.push_back(peer_dense);
+        }
     }
     long long made = 0;
     for (long long i = 0; i < n; ++i)
@@ -556,6 +590,8 @@ void pangulu_sm100_driver_commit(void* handle)
 {
     Handle* h = (Handle*)handle;
     if (!h->B.host_only) pangulu_sm100_plan_commit(h->plan);
+    h->barrier = g_barrier;
+    h->wired = true;
 }
 
 void pangulu_sm100_driver_gstrf_reset(void* handle) { pangulu_sm100_plan_reset(((Handle*)handle)->plan); }
@@ -567,10 +603,65 @@ long long pangulu_sm100_driver_trace(void* handle, unsigned long long* out, long
     return h->plan ? pangulu_sm100_plan_trace(h->plan, out, cap) : 0;
 }
 
+long long pangulu_sm100_driver_task_work(void* handle, float* out, long long cap)
+{
+    Handle* h = (Handle*)handle;
+    return h->plan ? pangulu_sm100_plan_task_work(h->plan, out, cap) : 0;
+}
+
 void pangulu_sm100_driver_download(void* handle)
 {
     Handle* h = (Handle*)handle;
     PSM(memcpy)(h->B.h_buf, h->B.d_buf, h->B.own_value_bytes, 1);
+}
+
+// The three passes of the reference's gstrf self-check (src/pangulu_numeric.c:1082-1341) over the blocks THIS rank owns;
+// the caller sums ux, then lux, over the ranks.  Complex types: real parts (the check vectors are real for real input).
+void pangulu_sm100_driver_check_ux(void* handle, double* ux)
+{
+    Handle* h = (Handle*)handle;
+    const BlockStore& B = h->B;
+    const int nb = B.nb;
+    for (const pangulu_storage_slot_t& s : B.slots)
+    {
+        if (s.bin_id != 0) continue;
+        const size_t r0 = (size_t)s.brow_pos * nb;
+        if (s.brow_pos == s.bcol_pos && s.is_upper)
+        {
+            for (int r = 0; r < nb; ++r)
+                for (iptr e = s.columnpointer[r]; e < s.columnpointer[r + 1]; ++e) ux[r0 + r] += t_real(((const T*)s.value)[e]);
+        }
+        else if (s.brow_pos < s.bcol_pos)
+        {
+            for (int c = 0; c < nb; ++c)
+                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) ux[r0 + s.rowindex[e]] += t_real(((const T*)s.value)[e]);
+        }
+    }
+}
+void pangulu_sm100_driver_check_lux(void* handle, const double* ux, double* lux)
+{
+    Handle* h = (Handle*)handle;
+    const BlockStore& B = h->B;
+    const int nb = B.nb;
+    const size_t N = (size_t)B.block_length * nb;
+    if (h->rank == 0)
+        for (size_t i = 0; i < N; ++i) lux[i] += ux[i];   // unit diagonal of L, counted once
+    for (const pangulu_storage_slot_t& s : B.slots)
+    {
+        if (s.bin_id != 0) continue;
+        const size_t r0 = (size_t)s.brow_pos * nb, c0 = (size_t)s.bcol_pos * nb;
+        if ((s.brow_pos == s.bcol_pos && !s.is_upper) || s.brow_pos > s.bcol_pos)
+            for (int c = 0; c < nb; ++c)
+                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) lux[r0 + s.rowindex[e]] += t_real(((const T*)s.value)[e]) * ux[c0 + c];
+    }
+}
+long long pangulu_sm100_driver_check_ax(void* handle, double* ax)
+{
+    Handle* h = (Handle*)handle;
+    const Csc& A = h->A_reordered;
+    for (eidx c = 0; c < A.n; ++c)
+        for (eptr e = A.ptr[c]; e < A.ptr[c + 1]; ++e) ax[A.idx[e]] += t_real(A.val[e]);
+    return (long long)A.n;
 }
 
 // || L (U 1) - A_reordered 1 ||_2 / || A_reordered 1 ||_2 from the host copies of the factors: the reference's

@@ -339,7 +339,7 @@ void build_schedule(BlockStore& B, Schedule& S)
 //   TSTRF  sum over entries (r,c) of B:            1 + 2 (|U(c,:)| - 1)
 //   GESSM  sum over entries (r,c) of B:            2 |L(:,r)|
 //   SSSSM  sum over entries (t,j) of B:            2 |A(:,t)|
-// (tests/test_flop_model.py checks the closed forms against the merge-based oracle and the reference's own
+// (tests/test_host_structure.py and tests/test_oracle.py check the closed forms against the merge-based oracle and the reference's own
 // -DPANGULU_PERF counter).  Bytes per task are the algorithmic figures of SURVEY.md 8(d).
 void work_model(const BlockStore& B, const Schedule& S, WorkModel& W)
 {

@@ -66,6 +66,7 @@ struct Options
     long long compact_block_threshold = 1;  // ... if both blocks have nnz/nb^2 >= this (per mille): the block-level rule decides who gets a compact copy
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
+    long long spin_timeout_ms = 30000;  // persistent executor: a dependency wait longer than this aborts the run with [PanguLU ERROR]
 };
 
 // pinned + device slab pair used to ship one batch's descriptors; recycled once its event fired
@@ -565,8 +566,9 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 else { big.push_back(G); big_slot.push_back(lo); }
                 if (eager_download)
                 {
-                    P.downloads.push_back({lo->value, lo->d_value, sizeof(T) * nl});
-                    P.downloads.push_back({up->value, up->d_value, sizeof(T) * nu});
+                    // (a grouped task owns the entries of its index range only: columns [c0,c1) of the lower, rows [c0,c1) of the upper half)
+                    P.downloads.push_back({(T*)lo->value + cb(lo, G.c0), (const T*)lo->d_value + cb(lo, G.c0), sizeof(T) * nl});
+                    P.downloads.push_back({(T*)up->value + cb(up, G.c0), (const T*)up->d_value + cb(up, G.c0), sizeof(T) * nu});
                     dl.count += 2;
                 }
                 ++j;
@@ -964,6 +966,8 @@ struct pangulu_sm100_plan
     std::unordered_map<const pangulu_storage_slot_t*, std::array<int, 4>> ddens_of;  // lower slot -> ddens index per group
     double stat_ct_pairtiles = 0, stat_ct_chunks = 0, stat_ct_dmma = 0, stat_ct_abytes = 0, stat_ct_tasks = 0, stat_ct_msum = 0, stat_ct_ntsum = 0;
     size_t dense_total_bytes = 0;
+    std::vector<float> ct_task_dmma;     // per compact-tile task: DMMA instructions (index = position in Program::ctasks)
+    std::vector<float> host_task_work;   // per task of the persistent executor: DMMA instructions (compact tiles), else 0
     // persistent executor
     bool mega = false;
     void* mega_buf = nullptr;
@@ -1058,6 +1062,8 @@ void build_mega(pangulu_sm100_plan* pl)
                 {
                     const CTileTask& ct = P.ctasks[c];
                     tasks.push_back({MEGA_CTILE, ct.dest, ct.clo | (ct.chi << 16), (int)(P.dests[ct.dest].pair_end - P.dests[ct.dest].pair_begin)});
+                    pl->host_task_work.resize(tasks.size(), 0.0f);
+                    if (c < pl->ct_task_dmma.size()) pl->host_task_work.back() = pl->ct_task_dmma[c];
                     const int4 di = dest_id[ct.dest];
                     remaining[di.x] += 1;
                     if (di.y >= 0) remaining[di.y] += 1;
@@ -1178,6 +1184,7 @@ void build_mega(pangulu_sm100_plan* pl)
     mp.scratch = (T*)q; q += sz_scratch;
     mp.trace = sz_trace ? (unsigned long long*)q : nullptr;
     pl->host_tasks = tasks;
+    pl->host_task_work.resize(tasks.size(), 0.0f);
     mp.dests = pl->D.dests;
     mp.pairs = pl->D.pairs;
     mp.getrf = pl->D.getrf;
@@ -1209,7 +1216,16 @@ void launch_mega(pangulu_sm100_plan* pl)
     Timer tm(K_MEGA);
     const size_t smem = (size_t)g.max_smem_optin - 512;  // (static shared memory of the kernel: tickets, mbarriers)
     pl->mp.smem_bytes = smem;  // whole SM: the shared-memory GETRF variant sizes itself against this
+    // the sparse SSSSM / panel tasks keep one dense vector of nb values per warp (16 warps) in shared memory
+    if ((size_t)16 * pl->nb * sizeof(T) + 4096 > smem)
+        fatal(__FILE__, __LINE__, "block size nb is too large for the persistent executor's per-warp shared-memory vectors; reduce init_options.nb or set option executor=0", nullptr);
     const int grid = g.sm_count;
+    {
+        const unsigned long long lim = (unsigned long long)std::max<long long>(1, g.opt.spin_timeout_ms) * 1000000ull;
+        const int zero_flag = 0;
+        CK(cudaMemcpyToSymbolAsync(g_spin_limit_ns, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyToSymbolAsync(g_abort, &zero_flag, sizeof zero_flag, 0, cudaMemcpyHostToDevice, g.stream));
+    }
     if (pl->nb <= 128)
     {
         CK(cudaFuncSetAttribute(mega_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1378,6 +1394,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "compact_block_threshold")) return &g.opt.compact_block_threshold;
     if (!strcmp(key, "cpanel")) return &g.opt.cpanel;
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
+    if (!strcmp(key, "spin_timeout_ms")) return &g.opt.spin_timeout_ms;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)
@@ -1650,6 +1667,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
         {
             const SsssmDest<T>& D2 = P.dests[ct.dest];
             pl->stat_ct_tasks += 1;
+            const double dmma_before = pl->stat_ct_dmma;
             for (u32 pp = D2.pair_begin; pp < D2.pair_end; ++pp)
             {
                 const DenseReg::Entry& ea = R.entries[P.cpairs[pp].a];
@@ -1666,6 +1684,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
                 pl->stat_ct_msum += ea.cnt;
                 pl->stat_ct_ntsum += nt;
             }
+            pl->ct_task_dmma.push_back((float)(pl->stat_ct_dmma - dmma_before));
         }
     }
     if (g.opt.executor == 1) build_mega(pl);
@@ -1716,6 +1735,17 @@ long long pangulu_sm100_plan_trace(pangulu_sm100_plan* pl, unsigned long long* o
         out[4 * i + 2] = tmp[3 * i + 1];
         out[4 * i + 3] = tmp[3 * i + 2];
     }
+    return n;
+}
+
+// per task of the persistent executor (same order as pangulu_sm100_plan_trace): DMMA instructions it issues (compact
+// tile tasks; 0 for the other kinds); returns the task count
+long long pangulu_sm100_plan_task_work(pangulu_sm100_plan* pl, float* out, long long cap)
+{
+    if (!pl || !pl->mega) return 0;
+    const long long n = (long long)pl->host_task_work.size();
+    if (out)
+        for (long long i = 0; i < n && i < cap; ++i) out[i] = pl->host_task_work[i];
     return n;
 }
 
@@ -1861,6 +1891,11 @@ int pangulu_sm100_ipc_export(void* devptr, void* handle64)
     CK(cudaIpcGetMemHandle(&h, devptr));
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
     memcpy(handle64, &h, 64);
+    return 0;
+}
+int pangulu_sm100_ipc_close(void* devptr)
+{
+    if (devptr) CK(cudaIpcCloseMemHandle(devptr));
     return 0;
 }
 int pangulu_sm100_ipc_open(const void* handle64, void** devptr)

@@ -219,8 +219,11 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             }
             st.armed = true;
         }
-        // the ring may hold generic-proxy writes of earlier tasks of this CTA; order them before the bulk copies
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // The ring may hold generic-proxy writes of earlier tasks of this CTA, and the compact operand copies in global
+        // memory were written with generic-proxy stores by the tasks that finished those blocks (possibly on another SM or,
+        // over NVLink, another GPU; their completion flags were acquired before this routine was entered): order both
+        // before the async-proxy reads of the bulk copies (cross-proxy fence, all state spaces).
+        asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
         if (tid < 256)
         {
@@ -734,7 +737,9 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     for (int ch = 0; ch < nb / 16; ++ch)
         if ((kmask >> ch) & 1u)
             for (int i = tid; i < 16 * LDX; i += 512) X[ch * 16 * LDX + i] = zero<T>();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // generic-proxy writes (X zeroing here; the dense triangular copies written by the GETRF / refresh task whose flag
+    // was acquired before this routine) before the async-proxy bulk reads
+    asm volatile("fence.proxy.async;" ::: "memory");
     __syncthreads();
     // producer: the column block of Tm for chunk J -> buffer `par`; one bulk copy per needed 16 x 16 sub-block
     auto issue = [&](int J, int par) {

@@ -1208,13 +1208,36 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p)
     return v;
 }
 __device__ __forceinline__ void st_release_sys(int* p, int v) { asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// Spin waits are bounded: a dependency that does not arrive within g_spin_limit_ns (a dead peer rank, CTAs that are
+// not co-resident under MPS/MIG, a scheduling bug) ends the run with the reference's error convention
+// (pangulu_platform_0201000.cu:31-50: print "[PanguLU ERROR]" and exit) instead of hanging every GPU: the waiting
+// thread prints, raises g_abort and traps, the launch fails and the host's CK() prints and exits.
+__device__ unsigned long long g_spin_limit_ns = 30ull * 1000ull * 1000ull * 1000ull;
+__device__ int g_abort = 0;
+__device__ __noinline__ void spin_timeout(const int* flag, int value)
+{
+    printf("[PanguLU ERROR] sm100 persistent executor: block %d waited more than %llu ms for a dependency (flag %p = %d); a peer rank died or the "
+           "executor's CTAs are not co-resident\n", (int)blockIdx.x, g_spin_limit_ns / 1000000ull, (const void*)flag, value);
+    atomicExch(&g_abort, 1);
+    __threadfence_system();
+    __trap();
+}
+// every 4096 polls (>= 1.6 ms once the back-off has reached 400 ns): compare the global timer with the first reading
+#define PSM_SPIN_GUARD(flag, value)                                                   \
+    if ((++polls & 4095u) == 0)                                                       \
+    {                                                                                 \
+        const unsigned long long now = global_ns();                                   \
+        if (t_first == 0) t_first = now;                                              \
+        else if (now - t_first > g_spin_limit_ns || g_abort) spin_timeout(flag, value); \
+    }
 __device__ __forceinline__ void spin_until_set(const int* flag, int multi = 0)
 {
-    unsigned ns = 20;
+    unsigned ns = 20, polls = 0;
+    unsigned long long t_first = 0;
     if (multi)
-        while (ld_acquire_sys(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+        while (ld_acquire_sys(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; PSM_SPIN_GUARD(flag, 0) }
     else
-        while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+        while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; PSM_SPIN_GUARD(flag, 0) }
 }
 // Whole CTA: copy the n finished values of a block into every peer mirror registered for sync id `id`, then raise
 // the peers' done flags.  Peer pointers are NVLink-mapped device pointers of other GPUs (CUDA IPC).
@@ -1246,8 +1269,10 @@ __device__ __forceinline__ void push_block(const int* push_ptr, const MegaPush<T
 }
 __device__ __forceinline__ void spin_until_zero(const int* cnt)
 {
-    unsigned ns = 20;
-    while (ld_acquire(cnt) != 0) { __nanosleep(ns); if (ns < 400) ns *= 2; }
+    unsigned ns = 20, polls = 0;
+    unsigned long long t_first = 0;
+    int v;
+    while ((v = ld_acquire(cnt)) != 0) { __nanosleep(ns); if (ns < 400) ns *= 2; PSM_SPIN_GUARD(cnt, v) }
 }
 
 // cooperative global -> shared copy of `bytes` bytes (both 16-byte aligned at the start), 128-bit accesses, 4 in flight
@@ -1357,6 +1382,7 @@ mega_kernel(const MegaParams<T> P)
                 __syncthreads();  // (the factors were written by other threads of this CTA)
                 diag_densify<T>(nb, G, P.dds[P.getrf_dd[mt.a]]);
             }
+            asm volatile("fence.proxy.async;" ::: "memory");   // the dense triangular copies are read with bulk copies (async proxy)
             __threadfence();
             __syncthreads();
             if (tid == 0) { st_release(P.done + id.x, 1); st_release(P.done + id.y, 1); }
@@ -1380,6 +1406,7 @@ mega_kernel(const MegaParams<T> P)
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             diag_densify<T>(nb, G, P.dds[P.getrf_dd[mt.a]]);
+            asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
             __syncthreads();
             if (tid == 0) st_release(P.done + mt.b, 1);
@@ -1402,6 +1429,7 @@ mega_kernel(const MegaParams<T> P)
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
             panel_compact_cta<T>(smem_raw, nb, Q, P.ops[Q.dense], P.dds[cpt.dd], cpt.r0, cp_state);
+            asm volatile("fence.proxy.async;" ::: "memory");   // the compact copy just written is read with bulk copies
             __threadfence();
             __syncthreads();
             if (tid == 0)
@@ -1434,7 +1462,8 @@ mega_kernel(const MegaParams<T> P)
             PanelTask<T> Q2 = Q;
             {
                 unsigned char* stage = smem_raw + (size_t)16 * nb * sizeof(T);
-                const size_t budget = P.smem_bytes - (size_t)16 * nb * sizeof(T);
+                const size_t vec_bytes = (size_t)16 * nb * sizeof(T);
+                const size_t budget = P.smem_bytes > vec_bytes ? P.smem_bytes - vec_bytes : 0;   // (launch_mega refuses nb that does not fit)
                 const u32 nd = Q.diag.ptr[nb];
                 const size_t need = (size_t)nd * (sizeof(T) + 2) + 4 * (size_t)(nb + 1) + 64;
                 if (need <= budget)
@@ -1456,6 +1485,7 @@ mega_kernel(const MegaParams<T> P)
             }
             const DenseOp<T>* dop = (P.ops && Q.dense >= 0) ? P.ops + Q.dense : nullptr;
             for (int rc = mt.b + warp; rc < mt.b + 64 && rc < nb; rc += 16) panel_solve_line<T>(nb, Q2, rc, x, dop);
+            asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
             __syncthreads();
             if (tid == 0)

@@ -139,6 +139,7 @@ class PanguLU:
         import torch.distributed as dist
 
         world, rank = dist.get_world_size(group), dist.get_rank(group)
+        self.L.pangulu_sm100_driver_disconnect(self._h)   # (a reconnect after rebuild_plan: drop the old peer mappings)
         table = self.mirror_table()
         handles = self.ipc_handles() if not self._host_only else bytes(192)
         gathered = [None] * world
@@ -164,6 +165,31 @@ class PanguLU:
 
     def factor_check(self) -> float:
         return float(self.L.pangulu_sm100_driver_factor_check(self._h))
+
+    def factor_check_distributed(self, group=None) -> float:
+        """||L(U 1) - A 1|| / ||A 1|| with the factors spread over the ranks of a torch.distributed group, in the
+        reference's own three passes (src/pangulu_numeric.c:1082-1341): every rank multiplies the blocks it owns
+        (host copies: call download() first), the partial vectors are summed over the ranks.  Same value on every rank."""
+        import torch
+        import torch.distributed as dist
+
+        N = int(self.info("block_length")) * self.nb
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+
+        def allsum(v):
+            t = torch.from_numpy(v).to(dev)
+            dist.all_reduce(t, group=group)
+            return t.cpu().numpy()
+
+        ux = np.zeros(N)
+        self.L.pangulu_sm100_driver_check_ux(self._h, ux.ctypes.data)
+        ux = np.ascontiguousarray(allsum(ux))
+        lux = np.zeros(N)
+        self.L.pangulu_sm100_driver_check_lux(self._h, ux.ctypes.data, lux.ctypes.data)
+        lux = allsum(lux)
+        ax = np.zeros(N)
+        n = int(self.L.pangulu_sm100_driver_check_ax(self._h, ax.ctypes.data))
+        return float(np.linalg.norm(lux[:n] - ax[:n]) / np.linalg.norm(ax[:n]))
 
     def perms(self) -> dict:
         n = self.n

@@ -46,6 +46,20 @@ for k in (0, 6):
     m = kind == k
     if m.any():
         print(names[k], "tasks: pairs total", npairs[m].sum(), "mean", npairs[m].mean().round(2), "max", npairs[m].max(), "| us per pair-tile", ((end[m]-start[m]).sum()/npairs[m].sum()).round(2))
+# efficiency of the compact tile tasks by task weight: DMMA instructions of the task at 16.1 cycles per instruction and SM
+# sub-partition (4 per SM) against the time the task held its SM
+wk = np.zeros(n, dtype=np.float32)
+if L.pangulu_sm100_driver_task_work(s._h, wk.ctypes.data, n) == n:
+    m = kind == 6
+    d, rt = wk[m].astype(np.float64), (end[m] - start[m]) * 1e-6
+    floor = d * 16.1 / 4 / 1.965e9
+    edges = [0, 1e3, 1e4, 1e5, 3e5, 1e6, 3e6, 1e7, 1e12]
+    print("compact tile tasks by DMMA count: [lo, hi)  tasks  share of DMMA  busy CTA-s  DMMA floor CTA-s  efficiency  mean pairs")
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        b = (d >= lo) & (d < hi)
+        if b.any():
+            print(f"  [{lo:8.0e},{hi:8.0e}) {b.sum():8d} {d[b].sum()/d.sum():6.3f} {rt[b].sum():9.2f} {floor[b].sum():9.2f} {floor[b].sum()/rt[b].sum():6.3f} {npairs[m][b].mean():8.1f}")
+    print(f"  all: busy {rt.sum():.2f} CTA-s, floor {floor.sum():.2f} CTA-s, efficiency {floor.sum()/rt.sum():.3f}")
 busy = (end - start).sum() / 1e3; waiting = (start - fetch).sum() / 1e3
 print(f"sum over CTAs: busy {busy:.1f} ms, waiting {waiting:.1f} ms, capacity 148 x span = {148*end.max()/1e3:.1f} ms")
 # critical chain through getrf tasks

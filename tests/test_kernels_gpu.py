@@ -209,7 +209,7 @@ def test_hybrid_batched_same_destination(vtype, ssssm_mode):
         arr = (_lib.Task * len(tasks))(*tasks)
         D.P("hybrid_batched")(nb, len(tasks), C.addressof(arr))
         D.P("synchronize")()
-        tol = TOL[vtype] * 10  # several updates accumulate
+        tol = TOL[vtype]
         for key, w in want.items():
             if key[0] == "d":
                 i = key[1]
@@ -275,7 +275,7 @@ def test_getrf_variants(make, nb, getrf_mode, vtype):
         arr = (_lib.Task * len(tasks))(*tasks)
         D.P("hybrid_batched")(nb, len(tasks), C.addressof(arr))  # all diagonal blocks in ONE batched launch
         D.P("synchronize")()
-        tol = TOL[vtype] * 4
+        tol = TOL[vtype]
         for (s_lo, s_up, nl, nu), (wl, wu) in zip(slots, want):
             assert rel_err(D.fetch(s_lo, nl), wl.value) <= tol
             assert rel_err(D.fetch(s_up, nu), wu.value) <= tol
