@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(_HERE, "lib")
+# (PANGULU_SM100_LIB_DIR: an instrumented build of the same library, e.g. lib_prof built with EXTRA=-DPSM_CT_PROFILE)
+LIB_DIR = os.environ.get("PANGULU_SM100_LIB_DIR") or os.path.join(_HERE, "lib")
 PLATFORM_ID = "0201001"
 
 VALUE_DTYPES = {"r64": np.float64, "r32": np.float32, "cr64": np.complex128, "cr32": np.complex64}

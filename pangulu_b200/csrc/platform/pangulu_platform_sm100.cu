@@ -256,6 +256,7 @@ struct DenseReg
     std::vector<Entry> entries;
     std::unordered_map<const pangulu_storage_slot_t*, int> index;
     std::vector<u16> meta;
+    std::unordered_map<std::string, size_t> meta_of_list;   // list content (+ operand side) -> its record in meta
     size_t dense_total = 0;
 
     int find(const pangulu_storage_slot_t* s) const
@@ -300,16 +301,27 @@ struct DenseReg
         e.kmask = kmask;
         e.dense_off = dense_total;
         dense_total += (e.dense_len + 3) & ~(size_t)3;  // keeps every copy 16-byte aligned for all value types
-        e.meta_off = meta.size();
-        meta.insert(meta.end(), list.begin(), list.end());
-        meta.insert(meta.end(), inv.begin(), inv.end());
-        if (as_b)
+        // Blocks with the same non-empty rows (columns) share ONE list record: the compact tile routine recognises
+        // consecutive operand pairs with identical maps by comparing the list pointers and keeps their products in the
+        // DMMA registers (sm100_compact.cuh, "runs").
+        std::string key(1, as_b ? 'b' : 'a');
+        key.append((const char*)list.data(), list.size() * sizeof(u16));
+        auto known = meta_of_list.find(key);
+        if (known != meta_of_list.end()) e.meta_off = known->second;
+        else
         {
-            u16 run = 0;
-            for (int c = 0; c <= nb; ++c)
+            e.meta_off = meta.size();
+            meta_of_list.emplace(std::move(key), e.meta_off);
+            meta.insert(meta.end(), list.begin(), list.end());
+            meta.insert(meta.end(), inv.begin(), inv.end());
+            if (as_b)
             {
-                meta.push_back(run);
-                if (c < nb && inv[c] != 0xffff) ++run;
+                u16 run = 0;
+                for (int c = 0; c <= nb; ++c)
+                {
+                    meta.push_back(run);
+                    if (c < nb && inv[c] != 0xffff) ++run;
+                }
             }
         }
         const int id = (int)entries.size();
@@ -1832,12 +1844,21 @@ void pangulu_sm100_plan_add_push3(pangulu_sm100_plan* pl, const void* d_value_lo
 double pangulu_sm100_plan_stat(pangulu_sm100_plan* pl, const char* key)
 {
     if (!pl || !key) return -1;
-    if (!strcmp(key, "ct_prof_on")) { int one = 1; CK(cudaMemcpyToSymbol(g_ct_prof_on, &one, sizeof one)); unsigned long long z[10] = {0}; CK(cudaMemcpyToSymbol(g_ct_prof, z, sizeof z)); return 0; }
+    // "ct_prof_on<n>": profile the compact tile tasks with at least n operand pairs (library built with -DPSM_CT_PROFILE)
+    if (!strncmp(key, "ct_prof_on", 10))
+    {
+        int on = key[10] ? atoi(key + 10) : 1;
+        CK(cudaMemcpyToSymbol(g_ct_prof_on, &on, sizeof on));
+        unsigned long long z[20] = {0};
+        CK(cudaMemcpyToSymbol(g_ct_prof, z, sizeof z));
+        return 0;
+    }
     if (!strncmp(key, "ct_prof", 7) && key[7] >= '0' && key[7] <= '9')
     {
-        unsigned long long v[10];
+        unsigned long long v[20];
         CK(cudaMemcpyFromSymbol(v, g_ct_prof, sizeof v));
-        return (double)v[key[7] - '0'];
+        const int k = atoi(key + 7);
+        return k < 20 ? (double)v[k] : -1.0;
     }
     if (!strcmp(key, "ct_tasks")) return pl->stat_ct_tasks;
     if (!strcmp(key, "ct_pairtiles")) return pl->stat_ct_pairtiles;

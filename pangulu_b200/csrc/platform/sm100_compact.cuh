@@ -100,7 +100,8 @@ struct CtLayout
     static constexpr size_t pc_bytes = (size_t)PSM_CT_BATCH * 48;
     static constexpr size_t item_off = pc_off + pc_bytes;
     static constexpr size_t rank_off = item_off + (size_t)PSM_CT_BATCH * 16 * 4;
-    static constexpr size_t total = rank_off + 256 + 2 * TN + 64;
+    static constexpr size_t map_off = rank_off + 256 + 2 * TN;          // per warp: 32 row + 32 column indices of its register tile
+    static constexpr size_t total = map_off + 16 * 64 * 2 + 64;
 };
 
 struct CtPairSm   // one staged operand pair (48 bytes)
@@ -110,37 +111,23 @@ struct CtPairSm   // one staged operand pair (48 bytes)
     const u16* rows;
     const u16* cols;       // already offset: + n0
     u16 m, ld, nt, nprime;
-    u32 kmask;
+    u32 kmask;             // k-chunks both operands have entries in; bit 31: the pair starts a new run (its row / column maps differ from the previous pair's)
     u32 first_item;
 };
+#define PSM_CT_RUNSTART 0x80000000u
 
-// tile-size traits: columns per destination tile and ring size (in chunks of the largest operands)
-template <class T> struct ct_traits { static constexpr int TN = 32, STAGES = 4; };
+// tile-size traits: columns per destination tile and ring size (in chunks of the largest operands).  A 64-column tile
+// halves the operand traffic of a 32-column one (every chunk of the left operand is streamed once per tile).
+template <class T> struct ct_traits { static constexpr int TN = 64, STAGES = 2; };                      // double: [64][258] accumulator + 2 x 42.5 KB
+template <> struct ct_traits<float> { static constexpr int TN = 64, STAGES = 4; };
+template <> struct ct_traits<pangulu_sm100_c32> { static constexpr int TN = 32, STAGES = 4; };
 template <> struct ct_traits<pangulu_sm100_c64> { static constexpr int TN = 16, STAGES = 2; };
 
 // DMMA inner products of one k-chunk with compile-time tile counts: the mma.sync instructions sit in straight-line code
-// (a predicated mma.sync costs a WARPSYNC each).  racc layout: [(mt*2 + slot)*2 + h], slot = column tile (tall grid) or
-// k4 parity (small grids).
-template <int TM>
-__device__ __forceinline__ void ct_chunk_small(double* racc, const double* Ap, const double* Bp, int ld)
-{
-#pragma unroll
-    for (int k4 = 0; k4 < PSM_CT_KC; k4 += 4)
-    {
-        const double b = Bp[k4];
-        double a[TM];
-#pragma unroll
-        for (int mt = 0; mt < TM; ++mt) a[mt] = Ap[k4 * ld + mt * 8];
-#pragma unroll
-        for (int mt = 0; mt < TM; ++mt)
-        {
-            const int slot = (k4 >> 2) & 1;
-            dmma884c(racc[(mt * 2 + slot) * 2], racc[(mt * 2 + slot) * 2 + 1], a[mt], b);
-        }
-    }
-}
+// (a predicated mma.sync costs a WARPSYNC each).  The warp's register tile is TM x TNC tiles of 8 x 8; racc layout:
+// [(mt*4 + nt2)*2 + h].  Per k4 step TM + TNC fragment loads feed TM * TNC tensor instructions.
 template <int TM, int TNC>
-__device__ __forceinline__ void ct_chunk_tall(double* racc, const double* Ap, const double* Bp, int ld)
+__device__ __forceinline__ void ct_chunk(double* racc, const double* Ap, const double* Bp, int ld)
 {
 #pragma unroll
     for (int k4 = 0; k4 < PSM_CT_KC; k4 += 4)
@@ -153,7 +140,18 @@ __device__ __forceinline__ void ct_chunk_tall(double* racc, const double* Ap, co
 #pragma unroll
         for (int mt = 0; mt < TM; ++mt)
 #pragma unroll
-            for (int nt2 = 0; nt2 < TNC; ++nt2) dmma884c(racc[(mt * 2 + nt2) * 2], racc[(mt * 2 + nt2) * 2 + 1], a[mt], b[nt2]);
+            for (int nt2 = 0; nt2 < TNC; ++nt2) dmma884c(racc[(mt * 4 + nt2) * 2], racc[(mt * 4 + nt2) * 2 + 1], a[mt], b[nt2]);
+    }
+}
+template <int TM>
+__device__ __forceinline__ void ct_chunk_n(int ntc, double* racc, const double* Ap, const double* Bp, int ld)
+{
+    switch (ntc)
+    {
+    case 1: ct_chunk<TM, 1>(racc, Ap, Bp, ld); break;
+    case 2: ct_chunk<TM, 2>(racc, Ap, Bp, ld); break;
+    case 3: ct_chunk<TM, 3>(racc, Ap, Bp, ld); break;
+    default: ct_chunk<TM, 4>(racc, Ap, Bp, ld); break;
     }
 }
 
@@ -163,12 +161,19 @@ struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
 
 // optional phase profile of the compact tile routine (warp 0 lane 0 of every CTA, clock64): prologue, staging, wait for
 // operands, compute, flush, pair setup, epilogue, produce
-__device__ unsigned long long g_ct_prof[10];
+__device__ unsigned long long g_ct_prof[20];   // [0,10): thread 0;  [10,20): the producer thread
 __device__ int g_ct_prof_on;
 
 // One CTA, one tile of the destination: the block columns [clo, chi).  The host cuts the tiles so that neither the
 // destination nor any B operand queued for it has more than TN NON-EMPTY columns in the range (compact column tiles:
-// a block with 40 non-empty columns has 2 tiles, not nb/TN).
+// a block with 40 non-empty columns has 1 tile, not nb/TN).
+//
+// RUNS.  The product of a pair lives in the warps' DMMA registers in the pair's COMPACT coordinates.  Consecutive pairs
+// whose row map (left operand) and column map (right operand) are the same arrays -- the host shares one list between all
+// blocks with the same non-empty rows / columns, so equal pointers mean equal maps; in the dense fronts of the big
+// separators all maps are the identity -- keep accumulating into the same registers: the tile behaves like one long-K
+// GEMM.  Only when the maps change (and after the last pair) are the registers added into the full-coordinate
+// accumulator tile in shared memory through the run's row / column lists (one block barrier per RUN, not per pair).
 struct CTileTask { int dest, clo, chi; };
 
 template <class T, int TN, int MAXST>
@@ -178,7 +183,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     typedef CtLayout<T, TN, MAXST> Lay;
     constexpr int KC = PSM_CT_KC, BLD = PSM_CT_BLD, LDC = Lay::LDC, NSLOT = PSM_CT_NSLOT;
     constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
-    static_assert(!kDouble || TN == 32, "DMMA warp grids assume 32-column tiles");
+    static_assert(!kDouble || TN == 64, "DMMA warp grids assume 64-column tiles");
+    static_assert(TN % 16 == 0 && TN <= 64, "tile width");
     constexpr int CPT = TN / 16;  // FMA path: columns per thread
     T* acc = reinterpret_cast<T*>(smem_raw);
     unsigned char* ring = smem_raw + Lay::acc_bytes;
@@ -187,17 +193,24 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     u32* items = reinterpret_cast<u32*>(smem_raw + Lay::item_off);  // (pair_in_batch << 16) | mask of the item's k-chunks (up to 4)
     unsigned char* crank = smem_raw + Lay::rank_off;                // [nb]: position of a column inside this tile, 0xff otherwise
     u16* ccols = reinterpret_cast<u16*>(smem_raw + Lay::rank_off + 256);  // [TN]: the tile's columns
-    __shared__ int s_nitems, s_slot_bytes, s_group, s_wcnt[8], s_ntc;
+    __shared__ int s_nitems, s_nst, s_group, s_wcnt[8], s_ntc;
 
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
+    u16* wrow = reinterpret_cast<u16*>(smem_raw + Lay::map_off) + warp * 64;   // [32] full rows of this warp's register tile (0xffff: none)
+    u16* wcol = wrow + 32;                                                      // [32] tile columns of it
     const bool diag = D.u.val != nullptr;
-    // the producer (bulk-copy issue, ~300 cycles per item) is lane 0 of the LAST warp: in the small warp grids that warp
-    // rarely has tensor work, so the issue cost stays off the busy warps
+    // the producer (bulk-copy issue, ~300 cycles per item) is lane 0 of the LAST warp
     constexpr int PTID = 480;
-    const bool prof = g_ct_prof_on != 0 && tid == 0;
+    // phase profile: compiled in only with -DPSM_CT_PROFILE (the ten 64-bit counters cost 20 registers per thread)
+#ifdef PSM_CT_PROFILE
+    // g_ct_prof_on = n: profile the tasks with at least n operand pairs (thread 0 and the producer thread)
+    const bool prof = g_ct_prof_on != 0 && (tid == 0 || tid == PTID) && (int)(D.pair_end - D.pair_begin) >= g_ct_prof_on;
     long long pt = prof ? clock64() : 0;
     unsigned long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto lap = [&](int k) { if (prof) { const long long now = clock64(); pacc[k] += (unsigned long long)(now - pt); pt = now; } };
+#else
+    auto lap = [](int) {};
+#endif
 
     // ---- task prologue: the tile's columns, a clear accumulator tile, armed barriers
     {
@@ -244,11 +257,120 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     // ---- thread roles
     const int lr = lane / 4, lk = lane % 4, lc = (lane % 4) * 2;
     const int tx = lane, ty = warp;                   // FMA: rows tx + 32 i, columns ty*CPT ..
-    constexpr int NACC = kDouble ? 16 : 8 * CPT;
+    constexpr int NACC = kDouble ? 32 : 8 * CPT;
     T racc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) racc[i] = zero<T>();
     u32 full_bits = st.full_bits, empty_bits = st.empty_bits;
+
+    // state of the current run (lives across descriptor batches)
+    int cur_m = 0, cur_nt = 0, cur_ld = 0;
+    int m_base = 0, n_base = 0, mtc = 0, ntc = 0;   // DMMA: this warp's piece of the run's compact product
+    bool active = false, have_run = false;
+    u16 rf8[kDouble ? 1 : 8], cf[kDouble ? 1 : CPT];   // FMA path: this thread's rows / columns
+    // staging warp: maps of the last pair with work, carried from batch to batch
+    const u16 *carry_rows = nullptr, *carry_cols = nullptr;
+
+    auto flush = [&]() {
+        // registers -> accumulator tile in full row coordinates.  Which warp owns an element of the tile depends on the
+        // run's compaction and warp grid, and warps drift apart by up to nst-1 items: the barrier keeps the adds of
+        // consecutive runs apart (every warp passes here once per run, with or without work).
+        __syncthreads();
+        if constexpr (kDouble)
+        {
+            if (active)
+            {
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+                {
+                    const u16 r = wrow[mt * 8 + lr];
+#pragma unroll
+                    for (int nt2 = 0; nt2 < 4; ++nt2)
+                    {
+                        const u32 c2 = *reinterpret_cast<const u32*>(wcol + nt2 * 8 + lc);   // two consecutive columns
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                        {
+                            const u32 c = h ? (c2 >> 16) : (c2 & 0xffffu);
+                            T& v = racc[(mt * 4 + nt2) * 2 + h];
+                            if (r != 0xffff && c != 0xffffu) acc[(int)c * LDC + r] += v;
+                            v = zero<T>();
+                        }
+                    }
+                }
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j)
+                {
+                    const u16 r = rf8[i], c = cf[j];
+                    T& v = racc[i * CPT + j];
+                    if (r != 0xffff && c != 0xffff) { T tv = acc[(int)c * LDC + r]; vadd(tv, v); acc[(int)c * LDC + r] = tv; }
+                    v = zero<T>();
+                }
+        }
+    };
+    // a new run: warp grid, this warp's piece, the row / column lists of its register tile
+    auto begin_run = [&](const CtPairSm& e) {
+        cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
+        if constexpr (kDouble)
+        {
+            // warp grid gm x gn (16 warps) by the run's tile counts: fewest tensor instructions on the busiest warp, then
+            // fewest fragment loads; at most 4 x 4 tiles of 8 x 8 per warp.  The row groups map onto the four SM
+            // sub-partitions (warp % 4), so narrow pairs still keep all four tensor pipes busy.
+            const int MT = (cur_m + 7) >> 3, NT = (cur_nt + 7) >> 3;
+            int best = 1 << 30, glog = 3;
+#pragma unroll
+            for (int g = 4; g >= 1; --g)   // gm = 16, 8, 4, 2
+            {
+                const int gm = 1 << g, gn = 16 >> g;
+                const int tm = (MT + gm - 1) >> g, tn = (NT + gn - 1) / gn;
+                const int cost = (tm <= 4 && tn <= 4) ? tm * tn * 16 + tm + tn : (1 << 30);
+                if (cost < best) { best = cost; glog = g; }
+            }
+            const int gm = 1 << glog, gn = 16 >> glog;
+            const int tm = (MT + gm - 1) >> glog, tn = (NT + gn - 1) / gn;
+            const int mi = warp & (gm - 1), ni = warp >> glog;
+            m_base = mi * tm * 8; n_base = ni * tn * 8;
+            mtc = min(tm, max(0, MT - mi * tm));
+            ntc = min(tn, max(0, NT - ni * tn));
+            // make the tile counts provably warp-uniform (vote results live in uniform registers)
+            mtc = __popc(__ballot_sync(PSM_FULL, lane < mtc));
+            ntc = __popc(__ballot_sync(PSM_FULL, lane < ntc));
+            active = mtc > 0 && ntc > 0;
+            if (active)
+            {
+                const int r = m_base + lane, c = n_base + lane;
+                wrow[lane] = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
+                u16 v = 0xffff;
+                if (lane < ntc * 8 && c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
+                wcol[lane] = v;
+            }
+            __syncwarp();
+        }
+        else
+        {
+            active = (cur_m > tx) && (ty * CPT < cur_nt);
+#pragma unroll
+            for (int i2 = 0; i2 < 8; ++i2)
+            {
+                const int r = tx + 32 * i2;
+                rf8[i2] = (active && r < cur_m) ? e.rows[r] : (u16)0xffff;
+            }
+#pragma unroll
+            for (int j = 0; j < CPT; ++j)
+            {
+                const int c = ty * CPT + j;
+                u16 v = 0xffff;
+                if (active && c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
+                cf[j] = v;
+            }
+        }
+    };
 
     lap(0);
     for (u32 pb = D.pair_begin; pb < D.pair_end; pb += PSM_CT_BATCH)
@@ -261,6 +383,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             u32 km = 0;
             int bytes = 0;
             CtPairSm e;
+            e.rows = nullptr; e.cols = nullptr;
             if (lane < npb)
             {
                 const CPair cp = cpairs[pb + lane];
@@ -276,16 +399,34 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 e.nt = (u16)min(n1 - n0, (u32)TN);
                 e.nprime = (u16)B.cnt;
                 km = (n1 > n0) ? (A.kmask & B.kmask) : 0u;
-                e.kmask = km;
                 if (km) bytes = (int)((KC * A.ld + e.nt * BLD) * sizeof(T));
             }
-            // an item = up to G k-chunks of one pair (one mbarrier hand-over, 2 G bulk copies): G from the largest chunk of
-            // the batch, so that 8 items fit the ring when chunks are small and 4 when they are not
+            // run boundaries: a pair with work continues the run of the previous pair with work iff both maps are the
+            // same arrays (and the same piece of the column list)
+            {
+                const unsigned wm = __ballot_sync(PSM_FULL, km != 0);
+                const unsigned below = wm & ((1u << lane) - 1u);
+                const int src = below ? 31 - __clz(below) : 0;
+                const unsigned long long pr = __shfl_sync(PSM_FULL, (unsigned long long)e.rows, src);
+                const unsigned long long pcl = __shfl_sync(PSM_FULL, (unsigned long long)e.cols, src);
+                const u16* prow = below ? (const u16*)pr : carry_rows;
+                const u16* pcol = below ? (const u16*)pcl : carry_cols;
+                const bool cont = km != 0 && prow == e.rows && pcol == e.cols;
+                if (wm)
+                {
+                    const int last = 31 - __clz(wm);
+                    carry_rows = (const u16*)__shfl_sync(PSM_FULL, (unsigned long long)e.rows, last);
+                    carry_cols = (const u16*)__shfl_sync(PSM_FULL, (unsigned long long)e.cols, last);
+                }
+                e.kmask = km | ((km != 0 && !cont) ? PSM_CT_RUNSTART : 0u);
+            }
+            // an item = up to G k-chunks of one pair (one mbarrier hand-over, 2 G bulk copies).  The ring is cut into 8, 4 or 2
+            // slots by the largest chunk of the batch.
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) bytes = max(bytes, __shfl_xor_sync(PSM_FULL, bytes, o));
             const int chunk_bytes = max(128, (bytes + 127) & ~127);
-            const int slot8 = (int)(Lay::ring_bytes / NSLOT), slot4 = (int)(Lay::ring_bytes / (MAXST >= 4 ? 4 : 2));
-            const int G = chunk_bytes <= slot8 ? min(4, slot8 / chunk_bytes) : min(4, max(1, slot4 / chunk_bytes));
+            const int nst = chunk_bytes * 8 <= (int)Lay::ring_bytes ? 8 : (chunk_bytes * 4 <= (int)Lay::ring_bytes ? 4 : 2);
+            const int G = min(4, (int)(Lay::ring_bytes / nst) / chunk_bytes);
             const int cnt = (__popc(km) + G - 1) / G;   // items of this lane's pair
             int off = cnt;
 #pragma unroll
@@ -294,7 +435,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 const int v = __shfl_up_sync(PSM_FULL, off, o);
                 if (lane >= o) off += v;
             }
-            if (lane == 31) { s_nitems = off; s_slot_bytes = G * chunk_bytes; s_group = G; }
+            if (lane == 31) { s_nitems = off; s_nst = nst; s_group = G; }
             off -= cnt;
             if (lane < npb)
             {
@@ -313,78 +454,13 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         lap(1);
         const int nitems = s_nitems;
         if (nitems == 0) continue;
-        const int slot_bytes = s_slot_bytes, G = s_group;
-        // pipeline depth: 8 slots when the batch's items fit an eighth of the ring, else 4 (>= MAXST by construction)
-        const int nst = ((size_t)slot_bytes * NSLOT <= Lay::ring_bytes) ? NSLOT : (MAXST >= 4 ? 4 : 2);
+        const int nst = s_nst, G = s_group;
+        const int slot_bytes = (int)(Lay::ring_bytes / nst) & ~127;
         // look-ahead nst-2, not nst-1: the slot a new item overwrites was released one full item earlier, so the producer
-        // (a lane of warp 0, which also computes) never waits for the slowest warp of the item just consumed
+        // (a lane of a warp that also computes) rarely waits for the slowest warp of the item just consumed
         const int smask = nst - 1, LA = nst > 2 ? nst - 2 : 1;
 
-        u16 rfull[4] = {0xffff, 0xffff, 0xffff, 0xffff}, cfull[4] = {0xffff, 0xffff, 0xffff, 0xffff};
-        u16 rf8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) rf8[i] = 0xffff;
-        int cur_m = 0, cur_nt = 0, cur_ld = 0;
-        int m_base = 0, n_base = 0, mtc = 0, ntc = 0;   // DMMA: this warp's piece of the current pair
-        bool small = false;                             // DMMA: 4 x 4 warp grid (one column group per warp, k-parity accumulators)
-        bool have_prev = false;
-
-        auto flush = [&]() {
-            // registers -> accumulator tile in full row coordinates.  Which warp owns an element of the tile depends on the
-            // pair's compaction, and warps drift apart by up to nst-1 items: the barrier keeps the adds of
-            // consecutive pairs apart (every warp passes here once per pair, with or without work).
-            __syncthreads();
-            if constexpr (kDouble)
-            {
-                if (mtc > 0 && ntc > 0)
-                {
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-                    {
-                        const u16 r = rfull[mt];
-                        if (small)
-                        {
-                            // the second column slot of the register tile held the odd k4 steps
-#pragma unroll
-                            for (int h = 0; h < 2; ++h)
-                            {
-                                const u16 c = cfull[h];
-                                if (r != 0xffff && c != 0xffff) acc[(int)c * LDC + r] += racc[(mt * 2) * 2 + h] + racc[(mt * 2 + 1) * 2 + h];
-                                racc[(mt * 2) * 2 + h] = 0.0;
-                                racc[(mt * 2 + 1) * 2 + h] = 0.0;
-                            }
-                        }
-                        else
-                        {
-#pragma unroll
-                            for (int nt2 = 0; nt2 < 2; ++nt2)
-#pragma unroll
-                                for (int h = 0; h < 2; ++h)
-                                {
-                                    const u16 c = cfull[nt2 * 2 + h];
-                                    T& v = racc[(mt * 2 + nt2) * 2 + h];
-                                    if (r != 0xffff && c != 0xffff) acc[(int)c * LDC + r] += v;
-                                    v = zero<T>();
-                                }
-                        }
-                    }
-                }
-            }
-            else
-            {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j)
-                    {
-                        const u16 r = rf8[i], c = cfull[j];
-                        T& v = racc[i * CPT + j];
-                        if (r != 0xffff && c != 0xffff) { T tv = acc[(int)c * LDC + r]; vadd(tv, v); acc[(int)c * LDC + r] = tv; }
-                        v = zero<T>();
-                    }
-            }
-        };
-        // producer step (thread 0): bulk copies of item i into its slot
+        // producer step: bulk copies of item i into its slot
         auto produce = [&](int i) {
             const int s = i & smask;
             lap(7);
@@ -415,86 +491,20 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         for (int pl = 0; pl < npb; ++pl)
         {
             const CtPairSm& e = pc[pl];
-            const int nchunk = __popc(e.kmask);
+            const u32 ekm = e.kmask;
+            const int nchunk = __popc(ekm & 0xffffu);
             const int cnt = (nchunk + G - 1) / G;   // items of this pair
             if (cnt == 0) continue;
-            lap(3);
-            if (have_prev) flush();
-            lap(4);
-            have_prev = true;
-            cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
-            bool active;
-            if constexpr (kDouble)
+            if (ekm & PSM_CT_RUNSTART)
             {
-                // warp grid by operand height: 8 x 2 warps of 32 x 16 (tall), else 4 x 4 warps of (8|16|32) x 8 -- the four
-                // row groups of the small grids sit on the four SM sub-partitions even when only one column group has work
-                const int mpad = (cur_m + 7) & ~7, MT = mpad / 8;
-                small = MT <= 16;
-                if (!small)
-                {
-                    m_base = (warp >> 1) * 32; n_base = (warp & 1) * 16;
-                    mtc = min(4, max(0, (mpad - m_base) / 8));
-                    ntc = min(2, max(0, (cur_nt + 7 - n_base) / 8));
-                }
-                else
-                {
-                    const int tm = (MT + 3) / 4;   // m-tiles per row group: the four groups (= SM sub-partitions) get equal shares
-                    m_base = (warp & 3) * tm * 8; n_base = (warp >> 2) * 8;
-                    mtc = min(tm, max(0, (mpad - m_base) / 8));
-                    ntc = cur_nt > n_base ? 1 : 0;
-                }
-                // make the tile counts provably warp-uniform (vote results live in uniform registers): otherwise every
-                // predicated mma.sync is preceded by a WARPSYNC
-                mtc = __popc(__ballot_sync(PSM_FULL, lane < mtc));
-                ntc = __popc(__ballot_sync(PSM_FULL, lane < ntc));
-                small = __all_sync(PSM_FULL, small);
-                active = mtc > 0 && ntc > 0;
-                if (active)
-                {
-#pragma unroll
-                    for (int mt = 0; mt < 4; ++mt)
-                    {
-                        const int r = m_base + mt * 8 + lr;
-                        rfull[mt] = (mt < mtc && r < cur_m) ? e.rows[r] : (u16)0xffff;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                    {
-                        const int c = n_base + (q >> 1) * 8 + lc + (q & 1);
-                        u16 v = 0xffff;
-                        if ((q >> 1) < ntc && c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
-                        cfull[q] = v;
-                    }
-                }
-            }
-            else
-            {
-                active = (cur_m > tx) && (ty * CPT < cur_nt);
-                if (active)
-                {
-#pragma unroll
-                    for (int i2 = 0; i2 < 8; ++i2)
-                    {
-                        const int r = tx + 32 * i2;
-                        rf8[i2] = r < cur_m ? e.rows[r] : (u16)0xffff;
-                    }
-#pragma unroll
-                    for (int j = 0; j < CPT; ++j)
-                    {
-                        const int c = ty * CPT + j;
-                        u16 v = 0xffff;
-                        if (c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
-                        cfull[j] = v;
-                    }
-                }
-                else
-                {
-#pragma unroll
-                    for (int i2 = 0; i2 < 8; ++i2) rf8[i2] = 0xffff;
-                }
+                lap(3);
+                if (have_run) flush();
+                lap(4);
+                have_run = true;
+                begin_run(e);
+                lap(5);
             }
             const bool warp_active = __any_sync(PSM_FULL, active);
-            lap(5);
             for (int j = 0; j < cnt; ++j, ++ci)
             {
                 if (tid == PTID && ci + LA < nitems) produce(ci + LA);
@@ -514,29 +524,12 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                         const double* Ap = As + lk * cur_ld + m_base + lr;
                         const double* Bp = Bs + (n_base + lr) * BLD + lk;
                         double* ra = reinterpret_cast<double*>(racc);
-                        if (small)
+                        switch (mtc)
                         {
-                            switch (mtc)
-                            {
-                            case 1: ct_chunk_small<1>(ra, Ap, Bp, cur_ld); break;
-                            case 2: ct_chunk_small<2>(ra, Ap, Bp, cur_ld); break;
-                            case 3: ct_chunk_small<3>(ra, Ap, Bp, cur_ld); break;
-                            default: ct_chunk_small<4>(ra, Ap, Bp, cur_ld); break;
-                            }
-                        }
-                        else
-                        {
-                            switch (mtc * 2 + ntc)
-                            {
-                            case 3: ct_chunk_tall<1, 1>(ra, Ap, Bp, cur_ld); break;
-                            case 4: ct_chunk_tall<1, 2>(ra, Ap, Bp, cur_ld); break;
-                            case 5: ct_chunk_tall<2, 1>(ra, Ap, Bp, cur_ld); break;
-                            case 6: ct_chunk_tall<2, 2>(ra, Ap, Bp, cur_ld); break;
-                            case 7: ct_chunk_tall<3, 1>(ra, Ap, Bp, cur_ld); break;
-                            case 8: ct_chunk_tall<3, 2>(ra, Ap, Bp, cur_ld); break;
-                            case 9: ct_chunk_tall<4, 1>(ra, Ap, Bp, cur_ld); break;
-                            default: ct_chunk_tall<4, 2>(ra, Ap, Bp, cur_ld); break;
-                            }
+                        case 1: ct_chunk_n<1>(ntc, ra, Ap, Bp, cur_ld); break;
+                        case 2: ct_chunk_n<2>(ntc, ra, Ap, Bp, cur_ld); break;
+                        case 3: ct_chunk_n<3>(ntc, ra, Ap, Bp, cur_ld); break;
+                        default: ct_chunk_n<4>(ntc, ra, Ap, Bp, cur_ld); break;
                         }
                     }
                     else
@@ -564,11 +557,9 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                   }
                 if (warp_active) __syncwarp();
                 if (lane == 0) mbar_arrive(bars + NSLOT + s);
+                lap(3);
             }
         }
-        lap(3);
-        if (have_prev) flush();
-        lap(4);
         // every release must be matched by a wait of the producer, so the barrier bits stay in step
         if (tid == PTID)
             for (int j = max(0, nitems - nst); j < nitems; ++j)
@@ -578,6 +569,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 empty_bits ^= 1u << s;
             }
     }
+    if (have_run) flush();
     st.full_bits = full_bits;
     st.empty_bits = empty_bits;
     lap(4);
@@ -621,8 +613,10 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     }
     __syncthreads();  // the accumulator tile is free again
     lap(6);
+#ifdef PSM_CT_PROFILE
     if (prof)
-        for (int k = 0; k < 10; ++k) atomicAdd(&g_ct_prof[k], pacc[k]);
+        for (int k = 0; k < 10; ++k) atomicAdd(&g_ct_prof[k + (tid == PTID ? 10 : 0)], pacc[k]);
+#endif
 }
 
 // stand-alone launch (per-wave executor): one CTA per tile task

@@ -151,9 +151,9 @@ class PanguLU:
             tb = np.ascontiguousarray(tb, dtype=np.int64)
             hb = (C.c_ubyte * 192).from_buffer_copy(hd)
             made += int(self.L.pangulu_sm100_driver_connect_peer(self._h, hb, tb.ctypes.data, len(tb)))
-        self.L.pangulu_sm100_driver_commit(self._h)
         self._barrier_cb = C.CFUNCTYPE(None)(lambda: dist.barrier(group))
         self.L.pangulu_sm100_driver_set_barrier(C.cast(self._barrier_cb, C.c_void_p))
+        self.L.pangulu_sm100_driver_commit(self._h)   # (the handle keeps the barrier installed at this point)
         dist.barrier(group)
         return made
 

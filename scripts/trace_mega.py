@@ -14,7 +14,7 @@ for kv in a.opt:
     k, v = kv.split("="); assert L.pangulu_sm100_set_option(k.encode(), int(v)) == 0
 s = PanguLU(matrices.poisson3d(a.size), nb=a.nb, mode=1, schedule=a.schedule, lookahead=a.lookahead)
 s.gstrf(); s.reset_values(True)
-if os.environ.get('CT_PROF'): s.info('plan_ct_prof_on')
+if os.environ.get('CT_PROF'): s.info('plan_ct_prof_on' + os.environ['CT_PROF'])
 t = s.gstrf()
 n = L.pangulu_sm100_driver_trace(s._h, None, 0)
 buf = np.zeros((n, 4), dtype=np.uint64)
@@ -37,10 +37,12 @@ if st["ct_pairtiles"] > 0:
           % (st["ct_tasks"], st["ct_pairtiles"], st["ct_chunks"] / st["ct_pairtiles"], st["ct_msum"] / st["ct_pairtiles"], st["ct_ntsum"] / st["ct_pairtiles"],
              st["ct_dmma"], st["ct_dmma"] * 16.1 / 4 / 1.965e9, st["ct_bytes"], st["dense_blocks"], st["dense_bytes"] / 1e9))
 if os.environ.get('CT_PROF'):
-    names7 = ["prologue", "staging", "wait_operands", "compute", "flush", "pair_setup", "epilogue", "other", "producer_wait_slot", "producer_issue"]
-    v = [s.info("plan_ct_prof%d" % k) for k in range(10)]
-    tot = sum(v)
-    print("compact tile phases (warp 0, cycles): " + "  ".join(f"{n} {x/tot*100:.1f}%" for n, x in zip(names7, v)) + f"  total {tot/1.965e9:.1f} CTA-s")
+    names7 = ["prologue", "staging", "wait_operands", "compute", "flush", "begin_run", "epilogue", "other", "producer_wait_slot", "producer_issue"]
+    for who, base in (("thread 0", 0), ("producer thread", 10)):
+        v = [s.info("plan_ct_prof%d" % (base + k)) for k in range(10)]
+        tot = sum(v)
+        if tot > 0:
+            print(f"compact tile phases, tasks with >= {os.environ['CT_PROF']} pairs ({who}, cycles): " + "  ".join(f"{n} {x/tot*100:.1f}%" for n, x in zip(names7, v)) + f"  total {tot/1.965e9:.1f} CTA-s")
 print(f"flop {s.info('flop'):.4e}  -> {s.info('flop')/t/1e9:.1f} GFLOP/s")
 for k in (0, 6):
     m = kind == k
