@@ -117,6 +117,17 @@ void pangulu_sm100_driver_check_ux(void *handle, double *ux);
 void pangulu_sm100_driver_check_lux(void *handle, const double *ux, double *lux);
 long long pangulu_sm100_driver_check_ax(void *handle, double *ax);
 
+/* The fast path behind PanguLU's own pangulu_gstrf (one rank): called INSTEAD of pangulu_numeric (src/pangulu.c:236-238)
+ * with the block slots PanguLU's storage layer built (storage->bins[0]: all off-diagonal blocks in block-CSC order, then a
+ * (lower, upper) pair per diagonal block, src/pangulu_storage.c:239-293).  Builds the static schedule and the device plan
+ * on the first call (cached per slot array), runs the persistent kernel on PanguLU's device arrays and refreshes PanguLU's
+ * host value arrays.  See INTEGRATION.md for the 12-line overlay that makes the call. */
+void pangulu_sm100_reference_gstrf(int nb, unsigned int n, unsigned int block_length, pangulu_storage_slot_t *slots, long long slot_count,
+                                   long long nondiag_slot_cnt);
+/* seconds: 0 schedule (first call), 1 plan creation (first call), 2 factorisation on the device (last call), 3 download */
+double pangulu_sm100_reference_gstrf_time(pangulu_storage_slot_t *slots, int which);
+void pangulu_sm100_reference_release(pangulu_storage_slot_t *slots);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,7 +69,8 @@ def main(argv=None):
     ap.add_argument("--no-solve", action="store_true")
     ap.add_argument("--no-blocks", action="store_true")
     ap.add_argument("--nthread", type=int, default=1)
-    ap.add_argument("--flavour", default="cpu", help="cpu: reference CPU platform; gpu: reference host code on top of the sm_100a module")
+    ap.add_argument("--flavour", default="cpu", help="cpu: reference CPU platform; gpu: reference host code on top of the sm_100a module; "
+                    "plan: the same plus the integration overlay (pangulu_gstrf -> this module's plan path)")
     a = ap.parse_args(argv)
     sys.path.insert(0, _ROOT)
     from oracle.ref import RefLib
@@ -84,6 +85,16 @@ def main(argv=None):
         _flatten(f.blocks(), "pre_", out)
     t = f.gstrf()
     out["t_gstrf"] = t
+    if a.flavour == "plan":
+        # the overlay's pangulu_gstrf ran this module's plan path: its phase times, and a second (warm: schedule and plan cached)
+        # factorisation after the values of A were put back into PanguLU's blocks
+        import ctypes as C
+
+        L = R.lib
+        L.pangulu_sm100_reference_gstrf_time.restype = C.c_double
+        L.pangulu_sm100_reference_gstrf_time.argtypes = [C.c_void_p, C.c_int]
+        slots = L.refh_slot(f.ctx, 0)
+        out["plan_times"] = np.array([L.pangulu_sm100_reference_gstrf_time(slots, k) for k in range(4)])
     out["flop"] = f.flop()
     out["blas"] = R.blas_backend
     if not a.no_blocks:

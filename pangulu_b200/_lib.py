@@ -48,6 +48,7 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_mirror_table", "pangulu_sm100_driver_connect_peer", "pangulu_sm100_driver_commit",
     "pangulu_sm100_driver_gstrf_reset", "pangulu_sm100_driver_gstrf_launch", "pangulu_sm100_driver_set_mode",
     "pangulu_sm100_driver_rebuild_plan", "pangulu_sm100_driver_diag_groups", "pangulu_sm100_driver_disconnect", "pangulu_sm100_driver_task_work",
+    "pangulu_sm100_reference_gstrf", "pangulu_sm100_reference_gstrf_time", "pangulu_sm100_reference_release",
     "pangulu_sm100_driver_check_ux", "pangulu_sm100_driver_check_lux", "pangulu_sm100_driver_check_ax",
 ]
 

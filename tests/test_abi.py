@@ -32,7 +32,7 @@ def test_headers_and_loader_agree():
     ext = set(re.findall(r"\b(pangulu_sm100_\w+)\(", text))
     assert ext == set(_lib.EXTENSION_FUNCTIONS)
     drv = open(os.path.join(ROOT, "include", "pangulu_sm100_driver.h")).read()
-    names = set(re.findall(r"\b(pangulu_(?:sm100_driver_\w+|init|gstrf|gstrs|gssv|finalize))\(", drv))
+    names = set(re.findall(r"\b(pangulu_(?:sm100_driver_\w+|sm100_reference_\w+|init|gstrf|gstrs|gssv|finalize))\(", drv))
     assert names == set(_lib.DRIVER_FUNCTIONS)
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.lib_path("r64")], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}

@@ -41,3 +41,34 @@ def test_reference_scheduler_on_sm100_platform(name, make, nb):
         worst = max(worst, rel_err(g.value, w.value))
     assert worst <= TOL["r64"], worst
     assert float(gpu["resid"]) <= max(4 * float(cpu["resid"]), 1e-15)
+
+
+PLAN_CASES = CASES + [("poisson3d-20-nb64", lambda: matrices.poisson3d(20), 64)]
+
+
+@pytest.mark.parametrize("name,make,nb", PLAN_CASES, ids=[c[0] for c in PLAN_CASES])
+def test_reference_gstrf_runs_the_plan_path(name, make, nb):
+    """The integration overlay (oracle/overlay/apply_overlay.py, 12 lines inside PanguLU's pangulu_gstrf): the reference's
+    own pangulu_init (its reordering, symbolic factorisation and block storage) followed by its pangulu_gstrf, which hands
+    the block storage to this module's static plan -- compact tile / compact panel kernels, independent groups of
+    diagonal blocks, persistent executor -- and the reference's own pangulu_gstrs on the returned factors."""
+    from oracle.ref import ref_available
+    from oracle.ref_run import run_reference, unflatten
+
+    if not (ref_available("r64", flavour="plan") and ref_available("r64", flavour="cpu")):
+        pytest.skip("oracle/_ref plan/CPU reference builds not present on this box")
+    A = make()
+    cpu = run_reference(A, nb, flavour="cpu")
+    gpu = run_reference(A, nb, flavour="plan")
+    assert np.array_equal(cpu["metis_perm"], gpu["metis_perm"])
+    want, got = unflatten(cpu, "post_", nb), unflatten(gpu, "post_", nb)
+    assert len(want) == len(got)
+    worst = 0.0
+    for g, w in zip(got, want):
+        assert (g.brow, g.bcol, g.is_upper) == (w.brow, w.bcol, w.is_upper)
+        assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)
+        assert np.isfinite(g.value).all()
+        worst = max(worst, rel_err(g.value, w.value))
+    assert worst <= TOL["r64"], worst
+    assert float(gpu["resid"]) <= max(4 * float(cpu["resid"]), 1e-15)
+    assert gpu["plan_times"][2] > 0, "pangulu_gstrf did not take the plan path"

@@ -67,3 +67,27 @@ def test_one_gpu_matches_reference(reference_factors, mode):
 def test_multi_rank_matches_reference(reference_factors, world):
     path, _ = reference_factors
     run_ranks(world, {"GRID": str(GRID), "NB": str(NB), "EXPECT": path}, timeout=900)
+
+
+def test_reference_gstrf_plan_path_matches_reference(reference_factors):
+    """Production granularity through the reference's OWN pangulu_init / pangulu_gstrf / pangulu_gstrs with the integration
+    overlay (tests/test_dropin_gpu.py): PanguLU's storage, this module's plan path underneath."""
+    from oracle.ref import ref_available
+    from oracle.ref_run import run_reference, unflatten
+
+    if not ref_available("r64", flavour="plan"):
+        pytest.skip("oracle/_ref plan build not present on this box")
+    _, z = reference_factors
+    gpu = run_reference(matrices.poisson3d(GRID), NB, flavour="plan")
+    assert np.array_equal(z["metis_perm"], gpu["metis_perm"])
+    want, got = unflatten(z, "post_", NB), unflatten(gpu, "post_", NB)
+    assert len(want) == len(got)
+    worst = 0.0
+    for g, w in zip(got, want):
+        assert (g.brow, g.bcol, g.is_upper) == (w.brow, w.bcol, w.is_upper)
+        assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)
+        worst = max(worst, rel_err(g.value, w.value))
+    assert worst <= TOL["r64"], worst
+    assert float(gpu["resid"]) <= max(4 * float(z["resid"]), 1e-15)
+    print("plan path behind the reference's pangulu_gstrf, 48^3 nb 256: schedule %.2f s, plan %.2f s, device %.3f s, download %.3f s; "
+          "reference CPU gstrf %.2f s" % (*[float(x) for x in gpu["plan_times"]], float(z["t_gstrf"])))
