@@ -72,6 +72,15 @@ class Oracle:
         self.lib.oracle_ssssm_diag(nb, p(lower.colptr), p(lower.rowidx), p(lower.value), p(upper.colptr), p(upper.rowidx),
                                    p(upper.value), p(a.colptr), p(a.rowidx), p(a.value), p(b.colptr), p(b.rowidx), p(b.value))
 
+    # solve-phase block kernels (pangulu_platform_0100000.c:433-506): y -= A x;  in-place triangular solve of a diagonal half
+    def spmv(self, nb, a, x, y):
+        p = self._p
+        self.lib.oracle_spmv(nb, p(a.colptr), p(a.rowidx), p(a.value), p(x), p(y))
+
+    def sptrsv(self, nb, s, x, uplo):
+        p = self._p
+        self.lib.oracle_sptrsv(nb, p(s.colptr), p(s.rowidx), p(s.value), p(x), int(uplo))
+
     def flop_getrf(self, nb, lower, upper):
         p = self._p
         return self.lib.oracle_getrf_flop(nb, p(lower.colptr), p(lower.rowidx), p(upper.colptr), p(upper.rowidx))

@@ -80,6 +80,10 @@ class RefLib:
         L.refh_gessm.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.refh_ssssm.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refh_transpose_with_valueidx.argtypes = [C.c_int] + [C.c_void_p] * 5
+        if hasattr(L, "refh_spmv"):
+            L.refh_spmv.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+            L.refh_vecadd.argtypes = [C.c_longlong, C.c_void_p, C.c_void_p]
+            L.refh_sptrsv.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
         L.refh_slot_offsets.argtypes = [C.c_void_p]
         L.pangulu_oracle_blas_backend.restype = C.c_char_p
         assert L.refh_sizeof_value() == self.dtype.itemsize

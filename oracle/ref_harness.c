@@ -322,6 +322,11 @@ void refh_ssssm(int nb, pangulu_storage_slot_t *c, pangulu_storage_slot_t *a, pa
     pangulu_platform_0100000_ssssm(nb, c, a, b, 0);
 }
 
+/* solve-phase block kernels of the CPU platform (pangulu_platform_0100000.c:433-506) */
+void refh_spmv(int nb, pangulu_storage_slot_t *a, calculate_type *x, calculate_type *y) { pangulu_platform_0100000_spmv(nb, a, x, y); }
+void refh_vecadd(long long n, calculate_type *b, calculate_type *x) { pangulu_platform_0100000_vecadd(n, b, x); }
+void refh_sptrsv(int nb, pangulu_storage_slot_t *s, calculate_type *x, long long uplo) { pangulu_platform_0100000_sptrsv(nb, s, x, uplo); }
+
 /* CSC -> CSR mirror with value index, the reference's own routine (src/pangulu_utils.c:479-511) */
 void refh_transpose_with_valueidx(int nb, pangulu_inblock_ptr *colptr, pangulu_inblock_idx *rowidx,
                                   pangulu_inblock_ptr *rowptr, pangulu_inblock_idx *colidx, pangulu_inblock_ptr *csr2csc)

@@ -109,6 +109,49 @@ def test_oracle_kernels_match_reference_platform_kernels(vtype):
     assert n_t and n_g and n_s
 
 
+@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64"])
+def test_oracle_solve_kernels_match_reference_platform_kernels(vtype):
+    """spmv / sptrsv of the solve phase (pangulu_platform_0100000.c:433-506): the oracle's restatement against the reference
+    CPU platform called directly, bit for bit (same operations in the same order)."""
+    from oracle.ref import RefLib, ref_available
+
+    if not ref_available(vtype):
+        pytest.skip("oracle/_ref not built on this box")
+    from helpers import blocks_of
+
+    nb = 16
+    dtype = np.dtype({"r64": np.float64, "r32": np.float32, "cr64": np.complex128}[vtype])
+    blocks = blocks_of(matrices.poisson3d(6), nb, vtype)
+    rng = np.random.default_rng(5)
+    rnd = lambda shape: (rng.uniform(-1, 1, shape) + (1j * rng.uniform(-1, 1, shape) if dtype.kind == "c" else 0)).astype(dtype)
+    for b in blocks:
+        b.value = rnd(b.value.shape)
+        if b.brow == b.bcol and b.is_upper:
+            b.value[b.colptr[:-1][np.diff(b.colptr.astype(np.int64)) > 0]] = 4.0
+    R, O = RefLib(vtype), Oracle(vtype)
+    if not hasattr(R.lib, "refh_spmv"):
+        pytest.skip("oracle/_ref predates the solve-kernel harness entries")
+    n_m = n_l = n_u = 0
+    for b in blocks:
+        slot = R.make_slot(b.brow, b.bcol, b.is_upper, b.colptr, b.rowidx, b.value, b.rowptr, b.colidx, b.csr2csc)
+        x = rnd(nb)
+        if b.brow != b.bcol:
+            y0 = rnd(nb)
+            yr, yo = y0.copy(), y0.copy()
+            R.lib.refh_spmv(nb, slot, x.ctypes.data, yr.ctypes.data)
+            O.spmv(nb, b, x, yo)
+            assert np.array_equal(yr, yo)
+            n_m += 1
+        else:
+            xr, xo = x.copy(), x.copy()
+            R.lib.refh_sptrsv(nb, slot, xr.ctypes.data, 1 if b.is_upper else 0)
+            O.sptrsv(nb, b, xo, 1 if b.is_upper else 0)
+            assert np.array_equal(xr, xo)
+            n_l += not b.is_upper
+            n_u += bool(b.is_upper)
+    assert n_m and n_l and n_u
+
+
 def test_oracle_block_lu_matches_live_reference():
     _live_ref()
     from oracle.ref_run import run_reference
