@@ -144,6 +144,16 @@ long long pangulu_sm100_plan_trace(pangulu_sm100_plan *plan, unsigned long long 
 /* per task, in the order of plan_trace: FP64 tensor (DMMA.8x8x4) instructions the task issues (compact tile tasks, else 0) */
 long long pangulu_sm100_plan_task_work(pangulu_sm100_plan *plan, float *out, long long cap);
 
+/* pangulu_gstrs on device-resident factors: the block forward / backward substitution of
+ * src/pangulu_sptrsv.c:24-174 with <id>_spmv / <id>_sptrsv semantics, one launch per block row and phase.  slots = every
+ * block the rank holds (off-diagonal blocks and both halves of the diagonal blocks); x_host has block_length*nb values
+ * (already permuted / scaled) and is overwritten with the solution.  Factors never return to the host. */
+typedef struct pangulu_sm100_solve_plan pangulu_sm100_solve_plan;
+pangulu_sm100_solve_plan *pangulu_sm100_solve_plan_create(pangulu_inblock_idx nb, pangulu_uint64_t block_length, pangulu_uint64_t nslot,
+                                                          pangulu_storage_slot_t **slots);
+void pangulu_sm100_solve_plan_execute(pangulu_sm100_solve_plan *plan, calculate_type *x_host);
+void pangulu_sm100_solve_plan_destroy(pangulu_sm100_solve_plan *plan);
+
 /* Multi-GPU wiring of a persistent plan (one rank per GPU).  A block finalised by its owner is written by the
  * producing kernel itself into the mirror copy every consumer rank keeps (peer-mapped pointers over NVLink /
  * NVSwitch, obtained with CUDA IPC), followed by a system-scope release of the consumer's "done" flag -- this

@@ -6,7 +6,7 @@
  *
  *     pangulu_init  -> reorder (METIS_NodeND when available) + symbolic + block storage + static schedule
  *     pangulu_gstrf -> numeric LU on the GPU through the platform C ABI (pangulu_platform_0201001.h)
- *     pangulu_gstrs -> block forward/backward substitution on the host copies of L and U
+ *     pangulu_gstrs -> block forward/backward substitution on the device-resident L and U (one rank)
  *
  * Out of scope here (kept as the reference's own code when the module is used inside PanguLU): MC64,
  * MPI distribution, the dynamic scheduler.  See DESIGN.md.
@@ -58,6 +58,8 @@ void pangulu_finalize(void **pangulu_handle);
  *   "schedule"        wave of an SSSSM update: 0 lazy (the wave that finalises its destination), 1 eager (first wave
  *                     after both operands are final), 2 (default) windowed: max(eager, destination's wave - "lookahead")
  *   "lookahead"       window of policy 2 in waves (default 2)
+ *   "device_solve"    1 (default): pangulu_gstrs runs the block substitution on the device-resident factors (only the
+ *                     right-hand side travels); 0: on the host copies of the factors, as the reference does
  *   "verbose"         1 prints the reference's info lines
  *   "host_only"       1 builds ordering/symbolic/blocks/schedule in host memory only (CPU-side tests of the
  *                     host logic); pangulu_gstrf on such a handle is a fatal error -- there is no CPU path

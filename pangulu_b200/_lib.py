@@ -37,6 +37,7 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_plan_add_push2", "pangulu_sm100_set_diag_groups", "pangulu_sm100_plan_stat",
     "pangulu_sm100_plan_flag_offset2", "pangulu_sm100_plan_expect_remote2", "pangulu_sm100_plan_add_push3",
     "pangulu_sm100_ipc_close", "pangulu_sm100_plan_task_work",
+    "pangulu_sm100_solve_plan_create", "pangulu_sm100_solve_plan_execute", "pangulu_sm100_solve_plan_destroy",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [

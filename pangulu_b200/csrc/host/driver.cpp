@@ -38,6 +38,7 @@ struct DriverConfig
     long long schedule = 2;
     long long lookahead = 2;
     long long split_diag = 1;  // schedule independent groups of diagonal blocks separately (single rank)
+    long long device_solve = 1;  // pangulu_gstrs: block substitution on the device-resident factors (0: on the host copies)
 };
 DriverConfig g_cfg;
 void (*g_barrier)(void) = nullptr;  // host barrier across ranks (multi-GPU), installed by the launcher
@@ -53,6 +54,8 @@ struct Handle
     Schedule sched;
     WorkModel work;
     pangulu_sm100_plan* plan = nullptr;
+    pangulu_sm100_solve_plan* solve_plan = nullptr;
+    bool device_solve = true;
     int mode = 0;
     int rank = 0, nproc = 1;  // fixed at pangulu_init (later driver_config calls configure FUTURE handles only)
     bool factored = false;
@@ -82,6 +85,7 @@ int pangulu_sm100_driver_config(const char* key, long long value)
     else if (k == "schedule") g_cfg.schedule = value;
     else if (k == "lookahead") g_cfg.lookahead = value;
     else if (k == "split_diag") g_cfg.split_diag = value;
+    else if (k == "device_solve") g_cfg.device_solve = value;
     else return -1;
     return 0;
 }
@@ -125,6 +129,7 @@ void pangulu_init(sparse_index_t pangulu_n, sparse_pointer_t pangulu_nnz, sparse
     }
     h->n = pangulu_n;
     h->mode = (int)g_cfg.mode;
+    h->device_solve = g_cfg.device_solve != 0;
     h->rank = (int)g_cfg.rank;
     h->nproc = (int)g_cfg.nproc;
     // several ranks: a peer may read any owned panel block through its compact dense copy
@@ -285,7 +290,8 @@ void pangulu_gstrs(sparse_value_t* rhs, pangulu_gstrs_options* gstrs_options, vo
         exit(EXIT_FAILURE);
     }
     const double t0 = wall_seconds();
-    if (h->mode == 1)
+    const bool on_device = h->device_solve && !h->B.host_only;
+    if (!on_device && h->mode == 1)
     {
         // resident mode keeps factors in HBM; the host solve needs them once
         PSM(memcpy)(h->B.h_buf, h->B.d_buf, h->B.own_value_bytes, 1);
@@ -294,7 +300,21 @@ void pangulu_gstrs(sparse_value_t* rhs, pangulu_gstrs_options* gstrs_options, vo
     // b' = P (Dr b): src/pangulu_reordering.c:683-697
     std::vector<T> x((size_t)h->B.block_length * h->nb, t_zero());
     for (eidx i = 0; i < n; ++i) x[h->R.metis_perm[h->R.row_perm[i]]] = t_mul(b[i], h->R.row_scale[i]);
-    solve_host(h->B, x);
+    if (on_device)
+    {
+        // the factors stay in HBM (every gstrf mode leaves the finished values in the device block buffer): block
+        // forward / backward substitution on the device, only the right-hand side travels
+        if (!h->solve_plan)
+        {
+            std::vector<pangulu_storage_slot_t*> sl;
+            for (pangulu_storage_slot_t& s : h->B.slots)
+                if (s.bin_id == 0) sl.push_back(&s);
+            h->solve_plan = pangulu_sm100_solve_plan_create((pangulu_inblock_idx)h->nb, h->B.block_length, sl.size(), sl.data());
+        }
+        pangulu_sm100_solve_plan_execute(h->solve_plan, (calculate_type*)x.data());
+    }
+    else
+        solve_host(h->B, x);
     // x = Dc P^T x': src/pangulu_reordering.c:699-713
     for (eidx i = 0; i < n; ++i) b[i] = t_mul(x[h->R.metis_perm[i]], h->R.col_scale[i]);
     h->times["gstrs"] = wall_seconds() - t0;
@@ -311,6 +331,7 @@ void pangulu_finalize(void** pangulu_handle)
     Handle* h = (Handle*)*pangulu_handle;
     if (!h) return;
     if (h->plan) pangulu_sm100_plan_destroy(h->plan);
+    if (h->solve_plan) pangulu_sm100_solve_plan_destroy(h->solve_plan);
     for (void* p : h->ipc_opened) pangulu_sm100_ipc_close(p);
     h->ipc_opened.clear();
     if (g_barrier == h->barrier) g_barrier = nullptr;   // (the callback usually belongs to the object that owns this handle)

@@ -1389,6 +1389,100 @@ void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t* s, calculate_ty
 // ------------------------------------------------------------------------------------------------------
 // Part 2: additive entry points
 // ------------------------------------------------------------------------------------------------------
+// Block substitution on device-resident factors: a solve plan is the list of off-diagonal blocks of every block row
+// (left of the diagonal for the forward sweep, right of it for the backward sweep) and the two diagonal halves.
+struct pangulu_sm100_solve_plan
+{
+    int nb = 0;
+    long long block_length = 0;
+    std::vector<long long> lptr, uptr;            // per block row: ranges into the device block lists
+    std::vector<Blk<T>> dlo, dup;                 // diagonal halves per block row (val == nullptr: not held)
+    SolveBlk<T>* d_l = nullptr;
+    SolveBlk<T>* d_u = nullptr;
+    T* d_x = nullptr;
+};
+
+pangulu_sm100_solve_plan* pangulu_sm100_solve_plan_create(pangulu_inblock_idx nb, pangulu_uint64_t block_length, pangulu_uint64_t nslot, pangulu_storage_slot_t** slots)
+{
+    ensure_ctx();
+    pangulu_sm100_solve_plan* sp = new pangulu_sm100_solve_plan();
+    sp->nb = nb;
+    sp->block_length = (long long)block_length;
+    std::vector<std::vector<SolveBlk<T>>> L(block_length), U(block_length);
+    Blk<T> none;
+    memset(&none, 0, sizeof none);
+    sp->dlo.assign(block_length, none);
+    sp->dup.assign(block_length, none);
+    for (pangulu_uint64_t i = 0; i < nslot; ++i)
+    {
+        const pangulu_storage_slot_t* s = slots[i];
+        if (s->brow_pos >= block_length || s->bcol_pos >= block_length) fatal(__FILE__, __LINE__, "block position outside the matrix in a solve plan", nullptr);
+        if (s->brow_pos == s->bcol_pos)
+        {
+            if (s->is_upper) sp->dup[s->brow_pos] = blk_upper_diag(s);
+            else sp->dlo[s->brow_pos] = blk_csc(s);
+            continue;
+        }
+        SolveBlk<T> b;
+        b.val = (const T*)s->d_value; b.ptr = s->d_columnpointer; b.idx = s->d_rowindex;
+        b.xoff = (long long)s->bcol_pos * nb;
+        (s->brow_pos > s->bcol_pos ? L : U)[s->brow_pos].push_back(b);
+    }
+    std::vector<SolveBlk<T>> fl, fu;
+    sp->lptr.assign(block_length + 1, 0);
+    sp->uptr.assign(block_length + 1, 0);
+    for (pangulu_uint64_t k = 0; k < block_length; ++k)
+    {
+        fl.insert(fl.end(), L[k].begin(), L[k].end());
+        fu.insert(fu.end(), U[k].begin(), U[k].end());
+        sp->lptr[k + 1] = (long long)fl.size();
+        sp->uptr[k + 1] = (long long)fu.size();
+    }
+    CK(cudaMalloc((void**)&sp->d_l, fl.size() * sizeof(SolveBlk<T>) + 256));
+    CK(cudaMalloc((void**)&sp->d_u, fu.size() * sizeof(SolveBlk<T>) + 256));
+    if (!fl.empty()) CK(cudaMemcpy(sp->d_l, fl.data(), fl.size() * sizeof(SolveBlk<T>), cudaMemcpyHostToDevice));
+    if (!fu.empty()) CK(cudaMemcpy(sp->d_u, fu.data(), fu.size() * sizeof(SolveBlk<T>), cudaMemcpyHostToDevice));
+    CK(cudaMalloc((void**)&sp->d_x, (size_t)block_length * nb * sizeof(T) + 256));
+    return sp;
+}
+
+// x (host, block_length * nb values, already permuted and scaled) <- U^-1 L^-1 x, all arithmetic on the device
+void pangulu_sm100_solve_plan_execute(pangulu_sm100_solve_plan* sp, calculate_type* x_host)
+{
+    if (!sp) fatal(__FILE__, __LINE__, "null solve plan", nullptr);
+    const int nb = sp->nb;
+    const size_t bytes = (size_t)sp->block_length * nb * sizeof(T);
+    CK(cudaMemcpyAsync(sp->d_x, x_host, bytes, cudaMemcpyHostToDevice, g.stream));
+    constexpr int THREADS = 256;
+    const size_t smem = (size_t)nb * sizeof(T);
+    set_smem(sptrsv_kernel<T, THREADS>, smem);
+    for (long long k = 0; k < sp->block_length; ++k)          // forward: x_k <- L_kk^-1 (x_k - sum_{j<k} L_kj x_j)
+    {
+        const long long nblk = sp->lptr[k + 1] - sp->lptr[k];
+        if (nblk) solve_spmv_row_kernel<T><<<(unsigned)nblk, 256, 0, g.stream>>>(nb, sp->d_l + sp->lptr[k], sp->d_x, k * nb);
+        if (sp->dlo[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dlo[k], sp->d_x + k * nb, 0);
+    }
+    for (long long k = sp->block_length - 1; k >= 0; --k)      // backward: x_k <- U_kk^-1 (x_k - sum_{j>k} U_kj x_j)
+    {
+        const long long nblk = sp->uptr[k + 1] - sp->uptr[k];
+        if (nblk) solve_spmv_row_kernel<T><<<(unsigned)nblk, 256, 0, g.stream>>>(nb, sp->d_u + sp->uptr[k], sp->d_x, k * nb);
+        if (sp->dup[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dup[k], sp->d_x + k * nb, 1);
+    }
+    CK_LAST();
+    g.launches[K_AUX] += 4 * sp->block_length;
+    CK(cudaMemcpyAsync(x_host, sp->d_x, bytes, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+}
+
+void pangulu_sm100_solve_plan_destroy(pangulu_sm100_solve_plan* sp)
+{
+    if (!sp) return;
+    if (sp->d_l) CK(cudaFree(sp->d_l));
+    if (sp->d_u) CK(cudaFree(sp->d_u));
+    if (sp->d_x) CK(cudaFree(sp->d_x));
+    delete sp;
+}
+
 static long long* option_slot(const char* key)
 {
     if (!key) return nullptr;

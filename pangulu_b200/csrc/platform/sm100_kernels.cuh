@@ -682,6 +682,32 @@ __global__ void __launch_bounds__(THREADS) sptrsv_kernel(int nb, Blk<T> S, T* __
     for (int i = threadIdx.x; i < nb; i += THREADS) xg[i] = x[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Block forward / backward substitution with the factors resident in HBM (pangulu_gstrs, src/pangulu_sptrsv.c:24-174 with
+// the block kernels above).  One launch per block row and phase instead of one per block:
+//   solve_spmv_row_kernel : x[row] -= sum over the row's off-diagonal blocks  A(row, j) x[j]   (CTA per block, warp per
+//                           column, FP reductions into the row's nb entries -- the sum order is free, as in the reference
+//                           with several ranks);
+//   sptrsv_kernel         : the row's diagonal half in place.
+// ------------------------------------------------------------------------------------------------
+template <class T> struct SolveBlk { const T* val; const u32* ptr; const u16* idx; long long xoff; };
+
+template <class T>
+__global__ void __launch_bounds__(256) solve_spmv_row_kernel(int nb, const SolveBlk<T>* __restrict__ blks, T* __restrict__ x, long long yoff)
+{
+    const SolveBlk<T> b = blks[blockIdx.x];
+    const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP;
+    T* y = x + yoff;
+    for (int col = warp; col < nb; col += 8)
+    {
+        const u32 e0 = col_begin(b.ptr, col), e1 = b.ptr[col + 1];
+        if (e0 == e1) continue;
+        const T xv = x[b.xoff + col];
+        if (is_zero(xv)) continue;
+        for (u32 e = e0 + lane; e < e1; e += PSM_WARP) atomic_sub(&y[b.idx[e]], vmul(b.val[e], xv));
+    }
+}
+
 // ================================================================================================
 // SSSSM, dense-tile path ("promoted" blocks: the only genuinely dense contraction of the factorisation).
 //

@@ -53,7 +53,7 @@ def driver_config(vtype: str = "r64", **kw) -> None:
 class PanguLU:
     def __init__(self, A, nb: int = 256, *, ordering: int = -1, mode: int = 0, rank: int = 0, nproc: int = 1,
                  host_only: bool = False, nthread: int = 1, verbose: bool = False, schedule: int = 2, lookahead: int = 2,
-                 split_diag: int = 1):
+                 split_diag: int = 1, device_solve: int = 1):
         """A: scipy.sparse matrix (any format; converted to sorted CSC) of dtype f64/f32/c128/c64."""
         import scipy.sparse as sp
 
@@ -67,7 +67,7 @@ class PanguLU:
         self.n = A.shape[0]
         self._host_only = bool(host_only)
         driver_config(self.vtype, ordering=ordering, mode=mode, rank=rank, nproc=nproc, host_only=int(host_only),
-                      verbose=int(verbose), schedule=schedule, lookahead=lookahead, split_diag=split_diag)
+                      verbose=int(verbose), schedule=schedule, lookahead=lookahead, split_diag=split_diag, device_solve=device_solve)
         self._colptr = np.ascontiguousarray(A.indptr, dtype=np.uint64)
         self._rowidx = np.ascontiguousarray(A.indices, dtype=np.uint32)
         self._value = np.ascontiguousarray(A.data, dtype=self.dtype)

@@ -282,3 +282,85 @@ def test_getrf_variants(make, nb, getrf_mode, vtype):
     finally:
         L.pangulu_sm100_set_option(b"getrf_mode", 0)
         D.close()
+
+
+@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64", "cr32"])
+def test_solve_kernels_against_oracle(vtype):
+    """spmv / sptrsv / vecadd of the platform interface (the solve-phase block kernels, reference CPU platform
+    pangulu_platform_0100000.c:433-506; the stock CUDA platform leaves them empty, ...0201000.cu:958-979) on device
+    slots against the oracle, every off-diagonal block and both halves of every diagonal block."""
+    O = _oracle(vtype)
+    dtype = np.dtype(_lib.VALUE_DTYPES[vtype])
+    nb = 32
+    blocks = blocks_of(matrices.poisson3d(8), nb, vtype)
+    rng = np.random.default_rng(11)
+    _randomise(blocks, rng, dtype)
+    D = DeviceBlocks(vtype, nb)
+    rnd = lambda n: (rng.uniform(-1, 1, n) + (1j * rng.uniform(-1, 1, n) if dtype.kind == "c" else 0)).astype(dtype)
+    tol = TOL[vtype]
+
+    def dev_vec(v):
+        p = C.c_void_p()
+        D.P("malloc")(C.byref(p), max(v.nbytes, 16))
+        D.P("memcpy")(p, v.ctypes.data, v.nbytes, 0)
+        return p
+
+    def fetch(p, n):
+        out = np.zeros(n, dtype=dtype)
+        D.P("memcpy")(out.ctypes.data, p, out.nbytes, 1)
+        return out
+
+    try:
+        n_m = n_l = n_u = 0
+        for b in blocks[:60] + [b for b in blocks if b.brow == b.bcol][:8]:
+            slot = D.slot(b)
+            x = rnd(nb)
+            if b.brow != b.bcol:
+                y = rnd(nb)
+                want = y.copy()
+                O.spmv(nb, b, x, want)
+                dx, dy = dev_vec(x), dev_vec(y)
+                D.P("spmv")(nb, C.addressof(slot), dx, dy)
+                D.P("synchronize")()
+                assert rel_err(fetch(dy, nb), want) <= tol
+                n_m += 1
+            else:
+                want = x.copy()
+                O.sptrsv(nb, b, want, 1 if b.is_upper else 0)
+                dx = dev_vec(x)
+                D.P("sptrsv")(nb, C.addressof(slot), dx, 1 if b.is_upper else 0)
+                D.P("synchronize")()
+                assert rel_err(fetch(dx, nb), want) <= tol
+                n_l += not b.is_upper
+                n_u += bool(b.is_upper)
+        assert n_m and n_l and n_u
+        a, c = rnd(1000), rnd(1000)
+        da, dc = dev_vec(a), dev_vec(c)
+        D.P("vecadd")(1000, da, dc)
+        D.P("synchronize")()
+        assert np.array_equal(fetch(da, 1000), a + c)
+    finally:
+        D.close()
+
+
+@pytest.mark.parametrize("vtype", ["r64", "cr64", "r32"])
+def test_gstrs_on_device_matches_host_solve(vtype):
+    """pangulu_gstrs with the factors resident in HBM (block substitution on the device, only the right-hand side travels)
+    against the same substitution on the host copies of the factors."""
+    from pangulu_b200 import PanguLU
+
+    dtype = np.dtype(_lib.VALUE_DTYPES[vtype])
+    A = (matrices.circuit_like(900, seed=3, dmax=16, dtype=dtype) if dtype.kind == "c" else matrices.poisson3d(12).astype(dtype))
+    n = A.shape[0]
+    b = (A @ np.ones(n, dtype=dtype)).astype(dtype)
+    xs = []
+    for dev in (1, 0):
+        s = PanguLU(A, nb=64, mode=1, device_solve=dev)
+        try:
+            s.gstrf()
+            xs.append(s.gstrs(b))
+        finally:
+            s.finalize()
+    tol = 1e-4 if "32" in vtype else 1e-12
+    assert np.linalg.norm(xs[0] - xs[1]) / np.linalg.norm(xs[1]) <= tol
+    assert np.linalg.norm(A @ xs[0] - b) / np.linalg.norm(b) <= tol
