@@ -488,6 +488,39 @@ void append_tasks(Program& P, int nb, const pangulu_task_t* tasks, size_t t0, si
                 st.kind = c == 0 ? K_SSSSM_TILE : c == 1 ? K_SSSSM_SPARSE : K_SSSSM_CTILE;
                 st.off = P.dests.size();
                 st.count = by_cls[c].size();
+                if (c == 2 && g.opt.split_pairs != 0 && by_cls[2].size() * 4 < (size_t)4 * g.sm_count)
+                {
+                    // A thin wave with heavy destinations -- the fronts of the top separators, where each of a few dozen
+                    // destinations has dozens of pending operand pairs -- would keep a handful of SMs busy for milliseconds on the
+                    // critical path while the rest idles (measured: the last 39 block columns of the 100^3 benchmark took ~4 ms
+                    // each at 4-60 % utilisation, profiles/r02_trace_tail_before_split.txt).  Cut the pair lists of such
+                    // destinations into pieces that run on different SMs; they combine through the global FP64 reductions all
+                    // compact tile tasks end with.
+                    size_t total_pairs = 0;
+                    for (auto& D0 : by_cls[2]) total_pairs += D0.pair_end - D0.pair_begin;
+                    const size_t per = std::max<size_t>(2, (total_pairs * 4 + (size_t)4 * g.sm_count - 1) / ((size_t)4 * g.sm_count));
+                    std::vector<SsssmDest<T>> split;
+                    std::vector<pangulu_storage_slot_t*> split_slot;
+                    for (size_t di = 0; di < by_cls[2].size(); ++di)
+                    {
+                        const SsssmDest<T>& D0 = by_cls[2][di];
+                        const u32 np = D0.pair_end - D0.pair_begin;
+                        if (np <= per + per / 2) { split.push_back(D0); split_slot.push_back(cslot[di]); continue; }
+                        const u32 npiece = (u32)((np + per - 1) / per);
+                        for (u32 q = 0; q < npiece; ++q)
+                        {
+                            SsssmDest<T> piece = D0;
+                            piece.pair_begin = D0.pair_begin + (u32)((size_t)np * q / npiece);
+                            piece.pair_end = D0.pair_begin + (u32)((size_t)np * (q + 1) / npiece);
+                            piece.flags |= 1u;
+                            split.push_back(piece);
+                            split_slot.push_back(cslot[di]);
+                        }
+                    }
+                    by_cls[2].swap(split);
+                    cslot.swap(split_slot);
+                    st.count = by_cls[2].size();
+                }
                 if (c == 2)
                 {
                     // cut every destination into column ranges in which neither the destination nor any of its B operands has

@@ -1265,28 +1265,60 @@ __device__ __forceinline__ void spin_until_set(const int* flag, int multi = 0)
     else
         while (ld_acquire(flag) == 0) { __nanosleep(ns); if (ns < 400) ns *= 2; PSM_SPIN_GUARD(flag, 0) }
 }
-// Whole CTA: copy the n finished values of a block into every peer mirror registered for sync id `id`, then raise
-// the peers' done flags.  Peer pointers are NVLink-mapped device pointers of other GPUs (CUDA IPC).
+// Whole CTA: `bytes` bytes from src to the same offset of up to 8 peer destinations (NVLink-mapped pointers), 128-bit
+// accesses where source and destinations are 16-byte aligned alike (block value arrays and compact copies are), every
+// source vector read ONCE and stored to all peers back to back so that the links to all peers are busy at the same time.
+__device__ __forceinline__ void peer_copy(char* const* dst, int nd, const char* src, size_t bytes)
+{
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    size_t head = (16 - ((size_t)src & 15)) & 15;
+    bool vec = true;
+    for (int d = 0; d < nd; ++d) vec = vec && (((size_t)dst[d] & 15) == ((size_t)src & 15));
+    if (!vec || head > bytes) head = bytes;   // no common alignment: word copies only
+    const size_t words_head = head / 4;       // (value types are multiples of 4 bytes)
+    for (size_t i = tid; i < words_head; i += nthr)
+    {
+        const unsigned v = reinterpret_cast<const unsigned*>(src)[i];
+        for (int d = 0; d < nd; ++d) reinterpret_cast<unsigned*>(dst[d])[i] = v;
+    }
+    const size_t nvec = (bytes - head) / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src + head);
+    for (size_t i = tid; i < nvec; i += nthr)
+    {
+        const uint4 v = s4[i];
+        for (int d = 0; d < nd; ++d) reinterpret_cast<uint4*>(dst[d] + head)[i] = v;
+    }
+    const size_t done = head + nvec * 16;
+    for (size_t i = done / 4 + tid; i < bytes / 4; i += nthr)
+    {
+        const unsigned v = reinterpret_cast<const unsigned*>(src)[i];
+        for (int d = 0; d < nd; ++d) reinterpret_cast<unsigned*>(dst[d])[i] = v;
+    }
+}
+// Whole CTA: copy the n finished values of a block (and its compact dense copy, where a peer reads the block through it)
+// into every peer mirror registered for sync id `id`, then raise the peers' done flags.  All pushes of one id cover the
+// same entry range (the whole block, or one independent group of a diagonal half).
 template <class T>
 __device__ __forceinline__ void push_block(const int* push_ptr, const MegaPush<T>* pushes, int id, const T* src, u32 n)
 {
     if (!push_ptr) return;
     const int e0 = push_ptr[id], e1 = push_ptr[id + 1];
     if (e0 == e1) return;
-    for (int e = e0; e < e1; ++e)
+    for (int eb = e0; eb < e1; eb += 8)
     {
-        T* dst = pushes[e].peer_val;
-        const bool whole = pushes[e].off == 0xffffffffu;
-        const u32 o = whole ? 0u : pushes[e].off, cnt = whole ? n : pushes[e].cnt;
-        for (u32 i = threadIdx.x; i < cnt; i += blockDim.x) dst[o + i] = src[o + i];
-        if (pushes[e].peer_dense)
-        {
-            // the consumer reads the block through its compact dense copy: same layout on both ranks
-            T* dd = pushes[e].peer_dense;
-            const T* sd = pushes[e].src_dense;
-            const size_t nd = pushes[e].dense_count;
-            for (size_t i = threadIdx.x; i < nd; i += blockDim.x) dd[i] = sd[i];
-        }
+        const int nd = min(8, e1 - eb);
+        const bool whole = pushes[eb].off == 0xffffffffu;
+        const u32 o = whole ? 0u : pushes[eb].off, cnt = whole ? n : pushes[eb].cnt;
+        char* dst[8];
+        for (int d = 0; d < nd; ++d) dst[d] = reinterpret_cast<char*>(pushes[eb + d].peer_val + o);
+        peer_copy(dst, nd, reinterpret_cast<const char*>(src + o), (size_t)cnt * sizeof(T));
+        int ndn = 0;
+        const T* sd = nullptr;
+        size_t nden = 0;
+        for (int d = 0; d < nd; ++d)
+            if (pushes[eb + d].peer_dense) { dst[ndn++] = reinterpret_cast<char*>(pushes[eb + d].peer_dense); sd = pushes[eb + d].src_dense; nden = pushes[eb + d].dense_count; }
+        // the consumers read the block through its compact dense copy: same layout on all ranks
+        if (ndn) peer_copy(dst, ndn, reinterpret_cast<const char*>(sd), nden * sizeof(T));
     }
     __threadfence_system();
     __syncthreads();

@@ -70,3 +70,15 @@ gs, ge = start[g], end[g]
 o = np.argsort(ge)
 print("getrf: last 10 ends (ms):", np.round(ge[o][-10:] / 1e3, 2))
 print("getrf completion gaps (us) percentiles 50/90/99:", np.percentile(np.diff(np.sort(ge)), [50, 90, 99]).round(1))
+
+# ---- the tail: what runs between the last GETRF tasks (the dense front of the top separator), and how busy the machine is
+last = o[-14:]
+print("tail of the factorisation: per interval between consecutive GETRF completions -> SM utilisation and task mix")
+for a_, b_ in zip(last[:-1], last[1:]):
+    t0_, t1_ = ge[a_], ge[b_]
+    inside = (end > t0_) & (start < t1_)
+    ov = np.minimum(end[inside], t1_) - np.maximum(start[inside], t0_)
+    util = ov.sum() / (148 * max(t1_ - t0_, 1e-9))
+    mix = {names[k]: (int(((kind == k) & inside).sum()), round(float(ov[kind[inside] == k].sum()) / 1e3, 2)) for k in range(9) if ((kind == k) & inside).any()}
+    gi = g[b_]
+    print(f"  [{t0_/1e3:8.2f}, {t1_/1e3:8.2f}] ms ({(t1_-t0_)/1e3:5.2f} ms) util {util:5.3f}  getrf run {(end[gi]-start[gi])/1e3:5.2f} ms wait {(start[gi]-fetch[gi])/1e3:5.2f} ms  tasks(count, busy ms): {mix}")
