@@ -107,6 +107,9 @@ void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t *s, calculate_ty
  *   "getrf_mode"      0 auto, 1 no shared-memory staging, 2 no dense promotion, 3 always dense-promoted (nb <= 256)
  *   "executor"        plans only: 1 (default) persistent megakernel -- one launch per factorisation, device-side
  *                     dependency flags; 0 one launch per kernel class per wave
+ *   "compact", "compact_threshold", "compact_block_threshold", "cpanel", "cpanel_block_threshold"
+ *                     plans only: which updates / panel solves take the compact dense paths (sm100_compact.cuh); defaults: every
+ *                     update, panel blocks of density >= 1 per mille
  *   "spin_timeout_ms" persistent executor: a dependency wait longer than this (default 30000) ends the run with
  *                     "[PanguLU ERROR] ..." and exit, the reference's error convention (…0201000.cu:31-50), instead of
  *                     hanging the GPU (dead peer rank, CTAs not co-resident)

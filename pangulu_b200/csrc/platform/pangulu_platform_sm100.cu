@@ -62,8 +62,12 @@ struct Options
     long long trace = 0;        // persistent executor: record per-task fetch/start/end timestamps (pangulu_sm100_plan_trace)
     long long executor = 1;     // plans: 1 persistent megakernel (one launch per factorisation), 0 one launch per kernel class per wave
     long long compact = 1;      // plans: SSSSM on compact dense operand copies (sm100_compact.cuh)
-    long long compact_threshold = 2;   // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path ...
-    long long compact_block_threshold = 1;  // ... if both blocks have nnz/nb^2 >= this (per mille): the block-level rule decides who gets a compact copy
+    // Every update takes the compact path by default (thresholds 0): measured at 100^3, routing the pairs of nearly empty
+    // blocks through the warp-per-column sparse kernel instead cost 9 % of the step (1.41 s vs 1.29 s)
+    long long compact_threshold = 0;   // per mille: pairs with sqrt(nnzA nnzB)/nb^2 >= this take the compact path ...
+    long long compact_block_threshold = 0;  // ... if both blocks have nnz/nb^2 >= this (per mille): the block-level rule decides who gets a compact copy
+    long long cpanel_block_threshold = 1;   // per mille: TSTRF/GESSM of blocks at least this dense run as dense triangular solves (compact panel); sparser ones
+                                            // use the warp-per-row/column sweep, which also fills the block's compact copy
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
     long long spin_timeout_ms = 30000;  // persistent executor: a dependency wait longer than this aborts the run with [PanguLU ERROR]
@@ -904,9 +908,9 @@ void launch_getrf_dense(int nb, const GetrfTask<T>* t, size_t n)
     const int nbp = (nb + 31) & ~31;
     T* scratch = ensure_scratch(n * (size_t)nbp * nbp * sizeof(T));
     Timer tm(K_GETRF);
-    const size_t smem = ((size_t)2 * PSM_GETRF_W * nbp + 64) * sizeof(T);
+    const size_t smem = ((size_t)2 * PSM_GETRF_W * (nbp + 4) + 64) * sizeof(T);
     set_smem(getrf_dense_kernel<T>, smem);
-    getrf_dense_kernel<T><<<(unsigned)n, 256, smem, g.stream>>>(nb, t, scratch);
+    getrf_dense_kernel<T><<<(unsigned)n, 512, smem, g.stream>>>(nb, t, scratch);
     CK_LAST();
     g.launches[K_GETRF]++;
 }
@@ -1532,6 +1536,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "compact_threshold")) return &g.opt.compact_threshold;
     if (!strcmp(key, "compact_block_threshold")) return &g.opt.compact_block_threshold;
     if (!strcmp(key, "cpanel")) return &g.opt.cpanel;
+    if (!strcmp(key, "cpanel_block_threshold")) return &g.opt.cpanel_block_threshold;
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     if (!strcmp(key, "spin_timeout_ms")) return &g.opt.spin_timeout_ms;
     return nullptr;
@@ -1637,9 +1642,11 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
         std::vector<const pangulu_storage_slot_t*> diag_of(P.panel.size(), nullptr);
         std::vector<char> compact(P.panel.size(), 0);
         std::vector<const pangulu_storage_slot_t*> remote_order;
+        const double cp_min = (double)g.opt.cpanel_block_threshold / 1000.0 * (double)nb * nb;
         for (size_t i = 0; i < P.panel.size(); ++i)
         {
             if (P.panel[i].dense < 0) continue;
+            if ((double)slot_nnz(nb, P.panel_slot[i]) < cp_min) continue;   // nearly empty block: the sparse sweep is cheaper
             const pangulu_storage_slot_t* lo = P.panel_diag_slot[i];
             const bool remote = lo->bin_id != 0;   // diagonal block factored by another rank: its halves arrive in mirror slots
             if (remote && g.opt.executor != 1) continue;

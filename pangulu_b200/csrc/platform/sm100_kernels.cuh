@@ -454,9 +454,11 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_
     (void)nb_block;
     const int off = G.c0, nb = G.c1 - G.c0;
     const int nbp = (nb + 31) & ~31;
-    T* Ls = reinterpret_cast<T*>(smem_raw);   // [W][nbp]  L panel (rows >= j0)
-    T* Us = Ls + W * nbp;                     // [W][nbp]  U12 rows of the panel
-    T* urow = Us + W * nbp;                   // [2][W+...] pivot row of the current column, double buffered
+    const int ldp = nbp + 4;                  // panel stride = 4 mod 8: conflict-free DMMA fragment loads
+    T* Ls = reinterpret_cast<T*>(smem_raw);   // [W][ldp]  L panel (rows >= j0)
+    T* Us = Ls + W * ldp;                     // [W][ldp]  U12 rows of the panel
+    T* urow = Us + W * ldp;                   // [2][W+...] pivot row of the current column, double buffered
+    constexpr bool kDouble = sizeof(T) == 8 && !is_complex<T>::value;
     const Blk<T> Lo = G.lower, Up = G.upper;  // Tm: column major, leading dimension nbp
     const int tid = threadIdx.x, warp = tid / PSM_WARP, lane = tid % PSM_WARP;
 
@@ -506,7 +508,7 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_
         {
 #pragma unroll
             for (int q = 0; q < W; ++q)
-                if (q < w) { Tm[(size_t)(j0 + q) * nbp + r] = p[q]; Ls[q * nbp + r] = p[q]; }
+                if (q < w) { Tm[(size_t)(j0 + q) * nbp + r] = p[q]; Ls[q * ldp + r] = p[q]; }
         }
         __syncthreads();
         const int t0 = j0 + w;  // first trailing row/column
@@ -521,13 +523,62 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_
             for (int q = 1; q < W; ++q)
 #pragma unroll
                 for (int s2 = 0; s2 < W; ++s2)
-                    if (s2 < q && q < w) fnma(u[q], Ls[s2 * nbp + j0 + q], u[s2]);
+                    if (s2 < q && q < w) fnma(u[q], Ls[s2 * ldp + j0 + q], u[s2]);
 #pragma unroll
             for (int q = 0; q < W; ++q)
-                if (q < w) { Tm[(size_t)c * nbp + j0 + q] = u[q]; Us[q * nbp + c] = u[q]; }
+                if (q < w) { Tm[(size_t)c * nbp + j0 + q] = u[q]; Us[q * ldp + c] = u[q]; }
         }
         __syncthreads();
-        // ---- trailing update T22 -= L21 U12, 4x4 register tile per thread: rows lane + 32 i, columns warp + NW j
+        // ---- trailing update T22 -= L21 U12
+        if constexpr (kDouble)
+        {
+            // FP64 tensor cores: every warp takes 16 x 16 pieces of the trailing matrix (2 x 2 DMMA tiles), reads them from the
+            // L2-resident scratch, subtracts the rank-16 product of the two panels (fragments from shared memory, A negated)
+            // and writes them back.  Rows / columns between nb and its multiple of 16 carry stale panel data; they only ever
+            // meet themselves and are not stored.
+            const int lr = lane / 4, lk = lane % 4;
+            const int ng = (nb - t0 + 15) / 16;
+            for (int gidx = warp; gidx < ng * ng; gidx += NW)
+            {
+                const int r0 = t0 + (gidx % ng) * 16, c0 = t0 + (gidx / ng) * 16;
+                double cf[2][2][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                        {
+                            const int rr2 = r0 + 8 * i + lr, cc2 = c0 + 8 * j + 2 * lk + h;
+                            cf[i][j][h] = (rr2 < nb && cc2 < nb) ? Tm[(size_t)cc2 * nbp + rr2] : 0.0;
+                        }
+#pragma unroll
+                for (int k4 = 0; k4 < W; k4 += 4)
+                {
+                    double a[2], b2[2];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) a[i] = -Ls[(k4 + lk) * ldp + r0 + 8 * i + lr];
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) b2[j] = Us[(k4 + lk) * ldp + c0 + 8 * j + lr];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) dmma884c(cf[i][j][0], cf[i][j][1], a[i], b2[j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                        {
+                            const int rr2 = r0 + 8 * i + lr, cc2 = c0 + 8 * j + 2 * lk + h;
+                            if (rr2 < nb && cc2 < nb) Tm[(size_t)cc2 * nbp + rr2] = cf[i][j][h];
+                        }
+            }
+        }
+        else
+        // 4x4 register tile per thread: rows lane + 32 i, columns warp + NW j
         for (int cb = t0; cb < nb; cb += 4 * NW)
             for (int rb = t0; rb < nb; rb += 128)
             {
@@ -548,9 +599,9 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_
                     {
                         T lv[4], uv[4];
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) lv[i] = rr[i] < nbp ? Ls[q * nbp + rr[i]] : zero<T>();
+                        for (int i = 0; i < 4; ++i) lv[i] = rr[i] < nbp ? Ls[q * ldp + rr[i]] : zero<T>();
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) uv[j] = cc[j] < nbp ? Us[q * nbp + cc[j]] : zero<T>();
+                        for (int j = 0; j < 4; ++j) uv[j] = cc[j] < nbp ? Us[q * ldp + cc[j]] : zero<T>();
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -575,13 +626,13 @@ __device__ __forceinline__ void getrf_dense_cta(unsigned char* smem_raw, int nb_
 }
 
 template <class T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 getrf_dense_kernel(int nb, const GetrfTask<T>* __restrict__ tasks, T* __restrict__ scratch_all)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbp = (nb + 31) & ~31;
     const GetrfTask<T> G = tasks[blockIdx.x];
-    getrf_dense_cta<T, 256>(smem_raw, nb, G, scratch_all + (size_t)blockIdx.x * nbp * nbp);
+    getrf_dense_cta<T, 512>(smem_raw, nb, G, scratch_all + (size_t)blockIdx.x * nbp * nbp);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -181,7 +181,7 @@ def test_gstrf_compact_dense_path(vtype, threshold, executor):
         resid = float(np.linalg.norm(A @ x - b) / np.linalg.norm(b))
         assert resid <= (1e-4 if "32" in vtype else 1e-12)
     finally:
-        L.pangulu_sm100_set_option(b"compact_threshold", 2)
-        L.pangulu_sm100_set_option(b"compact_block_threshold", 1)
+        L.pangulu_sm100_set_option(b"compact_threshold", 0)      # (the defaults)
+        L.pangulu_sm100_set_option(b"compact_block_threshold", 0)
         L.pangulu_sm100_set_option(b"executor", 1)
         s.finalize()
