@@ -119,6 +119,14 @@ void pangulu_sm100_driver_check_ux(void *handle, double *ux);
 void pangulu_sm100_driver_check_lux(void *handle, const double *ux, double *lux);
 long long pangulu_sm100_driver_check_ax(void *handle, double *ax);
 
+/* Factor files: the owned blocks in PanguLU's own packed block format (32-byte header, value / columnpointer / rowindex and,
+ * for strictly-lower blocks, the CSR mirror: src/pangulu_storage.c:295-357, src/pangulu_communication.c:1929-1942) behind a
+ * header with the permutations.  save returns the bytes written (-1: cannot open); load puts the values into a handle
+ * initialised on the same matrix (patterns and permutation are compared; a mismatch is a fatal error) and returns the number
+ * of blocks read: pangulu_init + load_factors + pangulu_gstrs solves without factoring again. */
+long long pangulu_sm100_driver_save_factors(void *handle, const char *path);
+long long pangulu_sm100_driver_load_factors(void *handle, const char *path);
+
 /* The fast path behind PanguLU's own pangulu_gstrf (one rank): called INSTEAD of pangulu_numeric (src/pangulu.c:236-238)
  * with the block slots PanguLU's storage layer built (storage->bins[0]: all off-diagonal blocks in block-CSC order, then a
  * (lower, upper) pair per diagonal block, src/pangulu_storage.c:239-293).  Builds the static schedule and the device plan

@@ -49,6 +49,7 @@ DRIVER_FUNCTIONS = [
     "pangulu_sm100_driver_mirror_table", "pangulu_sm100_driver_connect_peer", "pangulu_sm100_driver_commit",
     "pangulu_sm100_driver_gstrf_reset", "pangulu_sm100_driver_gstrf_launch", "pangulu_sm100_driver_set_mode",
     "pangulu_sm100_driver_rebuild_plan", "pangulu_sm100_driver_diag_groups", "pangulu_sm100_driver_disconnect", "pangulu_sm100_driver_task_work",
+    "pangulu_sm100_driver_save_factors", "pangulu_sm100_driver_load_factors",
     "pangulu_sm100_reference_gstrf", "pangulu_sm100_reference_gstrf_time", "pangulu_sm100_reference_release",
     "pangulu_sm100_driver_check_ux", "pangulu_sm100_driver_check_lux", "pangulu_sm100_driver_check_ax",
 ]
@@ -189,6 +190,9 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_plan_task_work.restype = C.c_longlong
     L.pangulu_sm100_driver_task_work.argtypes = [vp, vp, C.c_longlong]
     L.pangulu_sm100_driver_task_work.restype = C.c_longlong
+    for fn in (L.pangulu_sm100_driver_save_factors, L.pangulu_sm100_driver_load_factors):
+        fn.argtypes = [vp, C.c_char_p]
+        fn.restype = C.c_longlong
     L.pangulu_sm100_driver_disconnect.argtypes = [vp]
     L.pangulu_sm100_driver_check_ux.argtypes = [vp, vp]
     L.pangulu_sm100_driver_check_lux.argtypes = [vp, vp, vp]

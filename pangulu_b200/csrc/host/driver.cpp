@@ -685,6 +685,139 @@ long long pangulu_sm100_driver_check_ax(void* handle, double* ax)
     return (long long)A.n;
 }
 
+// ---- factor files ----------------------------------------------------------------------------
+// The owned blocks are written one after the other in PanguLU's OWN packed block format -- the image a block has in
+// bin 0 and on the wire (src/pangulu_storage.c:295-357; header src/pangulu_communication.c:1929-1942, SURVEY
+// Appendix A): 32-byte header {u64 nnz, u32 brow, u32 bcol, u32 is_upper, 12 bytes pad}, value[nnz], u32
+// columnpointer[nb+1], u16 rowindex[nnz], pad to 8, and for strictly-lower blocks u32 idx_of_csc_value_for_csr[nnz],
+// u32 rowpointer[nb+1], u16 columnindex[nnz], pad to 8 -- behind a file header with the permutations and scalings.
+// load_factors puts the values back into a handle initialised on the same matrix (patterns are compared entry by entry):
+// pangulu_init + load_factors + pangulu_gstrs solves without factoring again; the files also serve as golden vectors.
+namespace {
+struct FactorFileHeader
+{
+    char magic[8];
+    uint32_t version, value_type, sizeof_value, nb, n, block_length;
+    uint64_t nblocks;
+};
+struct WireHeader { uint64_t nnz; uint32_t brow, bcol, is_upper; unsigned char pad[12]; };
+static_assert(sizeof(WireHeader) == 32, "PanguLU block header");
+inline uint32_t value_type_code()
+{
+#if defined(CALCULATE_TYPE_CR64)
+    return 2;
+#elif defined(CALCULATE_TYPE_CR32)
+    return 3;
+#elif defined(CALCULATE_TYPE_R32)
+    return 1;
+#else
+    return 0;
+#endif
+}
+}  // namespace
+
+long long pangulu_sm100_driver_save_factors(void* handle, const char* path)
+{
+    Handle* h = (Handle*)handle;
+    const BlockStore& B = h->B;
+    const int nb = B.nb;
+    FILE* f = fopen(path, "wb");
+    if (!f) return -1;
+    FactorFileHeader fh;
+    memset(&fh, 0, sizeof fh);
+    memcpy(fh.magic, "PGLUF01", 8);
+    fh.version = 1; fh.value_type = value_type_code(); fh.sizeof_value = (uint32_t)sizeof(T); fh.nb = (uint32_t)nb; fh.n = h->n; fh.block_length = B.block_length;
+    for (const pangulu_storage_slot_t& s : B.slots) fh.nblocks += s.bin_id == 0;
+    long long bytes = 0;
+    auto put = [&](const void* p, size_t n) { if (n) bytes += (long long)fwrite(p, 1, n, f); };
+    put(&fh, sizeof fh);
+    put(h->R.metis_perm.data(), sizeof(eidx) * h->n);
+    put(h->R.row_perm.data(), sizeof(eidx) * h->n);
+    put(h->R.col_perm.data(), sizeof(eidx) * h->n);
+    put(h->R.row_scale.data(), sizeof(T) * h->n);
+    put(h->R.col_scale.data(), sizeof(T) * h->n);
+    const unsigned char zeros[8] = {0};
+    for (const pangulu_storage_slot_t& s : B.slots)
+    {
+        if (s.bin_id != 0) continue;
+        const size_t nnz = s.columnpointer[nb];
+        WireHeader wh;
+        memset(&wh, 0, sizeof wh);
+        wh.nnz = nnz; wh.brow = s.brow_pos; wh.bcol = s.bcol_pos; wh.is_upper = (uint32_t)s.is_upper;
+        put(&wh, sizeof wh);
+        put(s.value, sizeof(T) * nnz);
+        put(s.columnpointer, sizeof(iptr) * (nb + 1));
+        put(s.rowindex, sizeof(iidx) * nnz);
+        put(zeros, (8 - (sizeof(iptr) * (nb + 1) + sizeof(iidx) * nnz) % 8) % 8);
+        if (s.brow_pos > s.bcol_pos)
+        {
+            put(s.idx_of_csc_value_for_csr, sizeof(iptr) * nnz);
+            put(s.rowpointer, sizeof(iptr) * (nb + 1));
+            put(s.columnindex, sizeof(iidx) * nnz);
+            put(zeros, (8 - (sizeof(iptr) * nnz + sizeof(iptr) * (nb + 1) + sizeof(iidx) * nnz) % 8) % 8);
+        }
+    }
+    fclose(f);
+    return bytes;
+}
+
+long long pangulu_sm100_driver_load_factors(void* handle, const char* path)
+{
+    Handle* h = (Handle*)handle;
+    BlockStore& B = h->B;
+    const int nb = B.nb;
+    FILE* f = fopen(path, "rb");
+    if (!f) return -1;
+    auto fail = [&](const char* what) {
+        fprintf(stderr, "[PanguLU ERROR] factor file %s: %s\n", path, what);
+        exit(EXIT_FAILURE);
+    };
+    auto get = [&](void* p, size_t n) { if (n && fread(p, 1, n, f) != n) fail("truncated"); };
+    FactorFileHeader fh;
+    get(&fh, sizeof fh);
+    if (memcmp(fh.magic, "PGLUF01", 8) != 0 || fh.version != 1) fail("not a PanguLU sm100 factor file (version 1)");
+    if (fh.value_type != value_type_code() || fh.sizeof_value != sizeof(T)) fail("value type differs from this library's");
+    if ((int)fh.nb != nb || fh.n != h->n || fh.block_length != B.block_length) fail("matrix order / block size differ from the handle's");
+    std::vector<eidx> perm(h->n);
+    get(perm.data(), sizeof(eidx) * h->n);
+    if (memcmp(perm.data(), h->R.metis_perm.data(), sizeof(eidx) * h->n) != 0) fail("fill-reducing permutation differs from the handle's");
+    get(perm.data(), sizeof(eidx) * h->n);
+    get(perm.data(), sizeof(eidx) * h->n);
+    std::vector<T> scale(h->n);
+    get(scale.data(), sizeof(T) * h->n);
+    get(scale.data(), sizeof(T) * h->n);
+    std::vector<iptr> ptr(nb + 1);
+    std::vector<iidx> idx;
+    std::vector<unsigned char> skip;
+    long long loaded = 0;
+    for (pangulu_storage_slot_t& s : B.slots)
+    {
+        if (s.bin_id != 0) continue;
+        const size_t nnz = s.columnpointer[nb];
+        WireHeader wh;
+        get(&wh, sizeof wh);
+        if (wh.nnz != nnz || wh.brow != s.brow_pos || wh.bcol != s.bcol_pos || (s.brow_pos == s.bcol_pos && wh.is_upper != (uint32_t)s.is_upper))
+            fail("block order or size differs from the handle's");
+        get(s.value, sizeof(T) * nnz);
+        get(ptr.data(), sizeof(iptr) * (nb + 1));
+        idx.resize(nnz);
+        get(idx.data(), sizeof(iidx) * nnz);
+        if (memcmp(ptr.data(), s.columnpointer, sizeof(iptr) * (nb + 1)) != 0 || (nnz && memcmp(idx.data(), s.rowindex, sizeof(iidx) * nnz) != 0))
+            fail("nonzero pattern of a block differs from the handle's");
+        size_t rest = (8 - (sizeof(iptr) * (nb + 1) + sizeof(iidx) * nnz) % 8) % 8;
+        if (s.brow_pos > s.bcol_pos)
+            rest += sizeof(iptr) * nnz + sizeof(iptr) * (nb + 1) + sizeof(iidx) * nnz + (8 - (sizeof(iptr) * nnz + sizeof(iptr) * (nb + 1) + sizeof(iidx) * nnz) % 8) % 8;
+        skip.resize(rest);
+        get(skip.data(), rest);
+        ++loaded;
+    }
+    fclose(f);
+    if ((uint64_t)loaded != fh.nblocks) fail("block count differs from the handle's");
+    if (!B.host_only) PSM(memcpy)(B.d_buf, B.h_buf, B.own_value_bytes, 0);
+    h->factored = true;
+    return loaded;
+}
+
 // || L (U 1) - A_reordered 1 ||_2 / || A_reordered 1 ||_2 from the host copies of the factors: the reference's
 // own gstrf self-check (src/pangulu_numeric.c:1082-1341), single rank.
 double pangulu_sm100_driver_factor_check(void* handle)

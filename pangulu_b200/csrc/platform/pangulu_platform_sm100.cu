@@ -70,6 +70,7 @@ struct Options
                                             // use the warp-per-row/column sweep, which also fills the block's compact copy
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
+    long long ct_gmax = 4, ct_minst = 2;  // compact tile ring policy: chunks per item (at most), items the ring must hold (at least)
     long long spin_timeout_ms = 30000;  // persistent executor: a dependency wait longer than this aborts the run with [PanguLU ERROR]
 };
 
@@ -1274,6 +1275,9 @@ void launch_mega(pangulu_sm100_plan* pl)
         const int zero_flag = 0;
         CK(cudaMemcpyToSymbolAsync(g_spin_limit_ns, &lim, sizeof lim, 0, cudaMemcpyHostToDevice, g.stream));
         CK(cudaMemcpyToSymbolAsync(g_abort, &zero_flag, sizeof zero_flag, 0, cudaMemcpyHostToDevice, g.stream));
+        const int gmax = (int)std::min<long long>(16, std::max<long long>(1, g.opt.ct_gmax)), minst = (int)std::min<long long>(8, std::max<long long>(2, g.opt.ct_minst));
+        CK(cudaMemcpyToSymbolAsync(g_ct_gmax, &gmax, sizeof gmax, 0, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyToSymbolAsync(g_ct_minst, &minst, sizeof minst, 0, cudaMemcpyHostToDevice, g.stream));
     }
     if (pl->nb <= 128)
     {
@@ -1539,6 +1543,8 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "cpanel_block_threshold")) return &g.opt.cpanel_block_threshold;
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     if (!strcmp(key, "spin_timeout_ms")) return &g.opt.spin_timeout_ms;
+    if (!strcmp(key, "ct_gmax")) return &g.opt.ct_gmax;
+    if (!strcmp(key, "ct_minst")) return &g.opt.ct_minst;
     return nullptr;
 }
 int pangulu_sm100_set_option(const char* key, long long value)

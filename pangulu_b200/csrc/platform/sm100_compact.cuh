@@ -161,6 +161,7 @@ struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
 
 // optional phase profile of the compact tile routine (warp 0 lane 0 of every CTA, clock64): prologue, staging, wait for
 // operands, compute, flush, pair setup, epilogue, produce
+__device__ int g_ct_gmax = 4, g_ct_minst = 2;   // ring policy of the compact tile routine (options "ct_gmax", "ct_minst")
 __device__ unsigned long long g_ct_prof[20];   // [0,10): thread 0;  [10,20): the producer thread
 __device__ int g_ct_prof_on;
 
@@ -314,46 +315,73 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 }
         }
     };
+    // warp grid gm x gn (16 warps) of a run by its tile counts: fewest tensor instructions on the busiest warp, then fewest
+    // fragment loads; at most 4 x 4 tiles of 8 x 8 per warp.  The row groups map onto the four SM sub-partitions (warp % 4),
+    // so narrow pairs still keep all four tensor pipes busy.  Returns this warp's piece.
+    auto grid_of = [&](int m, int nt, int& mb, int& nbs, int& mc, int& nc) {
+        const int MT = (m + 7) >> 3, NT = (nt + 7) >> 3;
+        int best = 1 << 30, glog = 3;
+#pragma unroll
+        for (int g = 4; g >= 1; --g)   // gm = 16, 8, 4, 2
+        {
+            const int gm = 1 << g, gn = 16 >> g;
+            const int tm = (MT + gm - 1) >> g, tn = (NT + gn - 1) / gn;
+            const int cost = (tm <= 4 && tn <= 4) ? tm * tn * 16 + tm + tn : (1 << 30);
+            if (cost < best) { best = cost; glog = g; }
+        }
+        const int gm = 1 << glog, gn = 16 >> glog;
+        const int tm = (MT + gm - 1) >> glog, tn = (NT + gn - 1) / gn;
+        const int mi = warp & (gm - 1), ni = warp >> glog;
+        mb = mi * tm * 8; nbs = ni * tn * 8;
+        mc = min(tm, max(0, MT - mi * tm));
+        nc = min(tn, max(0, NT - ni * tn));
+    };
+    // The row / column indices of the NEXT run's register tile are fetched from global memory while the current pair is
+    // multiplied (pre_for = index in the batch of the pair they belong to): a run then starts without an L2 round trip.
+    int pre_for = -1;
+    u16 pre_row = 0xffff, pre_col = 0xffff;
+    auto prefetch_run = [&](const CtPairSm& e, int pl) {
+        if constexpr (kDouble)
+        {
+            int mb, nbs, mc, nc;
+            grid_of(e.m, e.nt, mb, nbs, mc, nc);
+            const int r = mb + lane, c = nbs + lane;
+            const bool act = mc > 0 && nc > 0;
+            pre_row = (act && lane < mc * 8 && r < e.m) ? e.rows[r] : (u16)0xffff;
+            pre_col = (act && lane < nc * 8 && c < e.nt) ? e.cols[c] : (u16)0xffff;
+            pre_for = pl;
+        }
+    };
     // a new run: warp grid, this warp's piece, the row / column lists of its register tile
-    auto begin_run = [&](const CtPairSm& e) {
+    auto begin_run = [&](const CtPairSm& e, int pl) {
         cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
         if constexpr (kDouble)
         {
-            // warp grid gm x gn (16 warps) by the run's tile counts: fewest tensor instructions on the busiest warp, then
-            // fewest fragment loads; at most 4 x 4 tiles of 8 x 8 per warp.  The row groups map onto the four SM
-            // sub-partitions (warp % 4), so narrow pairs still keep all four tensor pipes busy.
-            const int MT = (cur_m + 7) >> 3, NT = (cur_nt + 7) >> 3;
-            int best = 1 << 30, glog = 3;
-#pragma unroll
-            for (int g = 4; g >= 1; --g)   // gm = 16, 8, 4, 2
-            {
-                const int gm = 1 << g, gn = 16 >> g;
-                const int tm = (MT + gm - 1) >> g, tn = (NT + gn - 1) / gn;
-                const int cost = (tm <= 4 && tn <= 4) ? tm * tn * 16 + tm + tn : (1 << 30);
-                if (cost < best) { best = cost; glog = g; }
-            }
-            const int gm = 1 << glog, gn = 16 >> glog;
-            const int tm = (MT + gm - 1) >> glog, tn = (NT + gn - 1) / gn;
-            const int mi = warp & (gm - 1), ni = warp >> glog;
-            m_base = mi * tm * 8; n_base = ni * tn * 8;
-            mtc = min(tm, max(0, MT - mi * tm));
-            ntc = min(tn, max(0, NT - ni * tn));
+            grid_of(cur_m, cur_nt, m_base, n_base, mtc, ntc);
             // make the tile counts provably warp-uniform (vote results live in uniform registers)
             mtc = __popc(__ballot_sync(PSM_FULL, lane < mtc));
             ntc = __popc(__ballot_sync(PSM_FULL, lane < ntc));
             active = mtc > 0 && ntc > 0;
             if (active)
             {
-                const int r = m_base + lane, c = n_base + lane;
-                wrow[lane] = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
+                u16 r16, c16;
+                if (pre_for == pl) { r16 = pre_row; c16 = pre_col; }
+                else
+                {
+                    const int r = m_base + lane, c = n_base + lane;
+                    r16 = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
+                    c16 = (lane < ntc * 8 && c < cur_nt) ? e.cols[c] : (u16)0xffff;
+                }
+                wrow[lane] = r16;
                 u16 v = 0xffff;
-                if (lane < ntc * 8 && c < cur_nt) { const unsigned char rk = crank[e.cols[c]]; if (rk != 0xff) v = rk; }
+                if (c16 != 0xffff) { const unsigned char rk = crank[c16]; if (rk != 0xff) v = rk; }
                 wcol[lane] = v;
             }
             __syncwarp();
         }
         else
         {
+            (void)pl;
             active = (cur_m > tx) && (ty * CPT < cur_nt);
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2)
@@ -425,8 +453,11 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) bytes = max(bytes, __shfl_xor_sync(PSM_FULL, bytes, o));
             const int chunk_bytes = max(128, (bytes + 127) & ~127);
-            const int nst = chunk_bytes * 8 <= (int)Lay::ring_bytes ? 8 : (chunk_bytes * 4 <= (int)Lay::ring_bytes ? 4 : 2);
-            const int G = min(4, (int)(Lay::ring_bytes / nst) / chunk_bytes);
+            // Hand-overs cost a few hundred cycles each (mbarrier round trip, dispatch): as many chunks per item as the ring
+            // allows (at most g_ct_gmax) while it still holds g_ct_minst items; then as many slots as fit (at most 8).
+            int G = g_ct_gmax;
+            while (G > 1 && (int)Lay::ring_bytes / (G * chunk_bytes) < g_ct_minst) --G;
+            const int nst = min(NSLOT, max(2, (int)Lay::ring_bytes / (G * chunk_bytes)));
             const int cnt = (__popc(km) + G - 1) / G;   // items of this lane's pair
             int off = cnt;
 #pragma unroll
@@ -458,11 +489,12 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         const int slot_bytes = (int)(Lay::ring_bytes / nst) & ~127;
         // look-ahead nst-2, not nst-1: the slot a new item overwrites was released one full item earlier, so the producer
         // (a lane of a warp that also computes) rarely waits for the slowest warp of the item just consumed
-        const int smask = nst - 1, LA = nst > 2 ? nst - 2 : 1;
+        const int LA = nst > 2 ? nst - 2 : 1;
+        pre_for = -1;   // (pair indices are per batch)
 
         // producer step: bulk copies of item i into its slot
         auto produce = [&](int i) {
-            const int s = i & smask;
+            const int s = i % nst;
             lap(7);
             if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
             lap(8);
@@ -501,15 +533,21 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 if (have_run) flush();
                 lap(4);
                 have_run = true;
-                begin_run(e);
+                begin_run(e, pl);
                 lap(5);
+            }
+            // next run of this batch: start its index loads now
+            {
+                int nx = pl + 1;
+                while (nx < npb && (pc[nx].kmask & 0xffffu) == 0) ++nx;
+                if (nx < npb && (pc[nx].kmask & PSM_CT_RUNSTART)) prefetch_run(pc[nx], nx);
             }
             const bool warp_active = __any_sync(PSM_FULL, active);
             for (int j = 0; j < cnt; ++j, ++ci)
             {
                 if (tid == PTID && ci + LA < nitems) produce(ci + LA);
                 lap(7);
-                const int s = ci & smask;
+                const int s = ci % nst;
                 mbar_wait(bars + s, (full_bits >> s) & 1u);
                 full_bits ^= 1u << s;
                 lap(2);
@@ -564,7 +602,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         if (tid == PTID)
             for (int j = max(0, nitems - nst); j < nitems; ++j)
             {
-                const int s = j & smask;
+                const int s = j % nst;
                 mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u);
                 empty_bits ^= 1u << s;
             }

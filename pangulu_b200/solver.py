@@ -163,6 +163,20 @@ class PanguLU:
         ng = int(self.L.pangulu_sm100_driver_diag_groups(self._h, int(k), b))
         return [int(b[i]) for i in range(ng + 1)]
 
+    def save_factors(self, path: str) -> int:
+        """Write the owned blocks (host copies: call download() first in resident mode) in PanguLU's packed block format."""
+        n = int(self.L.pangulu_sm100_driver_save_factors(self._h, str(path).encode()))
+        if n < 0:
+            raise OSError(f"cannot write {path}")
+        return n
+
+    def load_factors(self, path: str) -> int:
+        """Put the values of a factor file into this handle (same matrix, same nb): gstrs works without gstrf."""
+        n = int(self.L.pangulu_sm100_driver_load_factors(self._h, str(path).encode()))
+        if n < 0:
+            raise OSError(f"cannot read {path}")
+        return n
+
     def factor_check(self) -> float:
         return float(self.L.pangulu_sm100_driver_factor_check(self._h))
 

@@ -185,3 +185,28 @@ def test_gstrf_compact_dense_path(vtype, threshold, executor):
         L.pangulu_sm100_set_option(b"compact_block_threshold", 0)
         L.pangulu_sm100_set_option(b"executor", 1)
         s.finalize()
+
+
+def test_factor_file_resolve_without_refactoring(tmp_path):
+    """pangulu_init + load_factors + pangulu_gstrs: a second handle of the same matrix solves with the factors a first
+    handle wrote to a file (PanguLU's packed block format), without running gstrf."""
+    A = matrices.poisson3d(12)
+    n = A.shape[0]
+    b = A @ np.ones(n)
+    s = PanguLU(A, nb=64, mode=1)
+    path = tmp_path / "factors.pglu"
+    try:
+        s.gstrf()
+        s.download()
+        x0 = s.gstrs(b)
+        s.save_factors(path)
+    finally:
+        s.finalize()
+    t = PanguLU(A, nb=64, mode=1)
+    try:
+        assert t.load_factors(path) == int(t.info("num_slots"))
+        x1 = t.gstrs(b)
+    finally:
+        t.finalize()
+    assert np.array_equal(x0, x1) or np.linalg.norm(x0 - x1) / np.linalg.norm(x0) < 1e-13
+    assert np.linalg.norm(A @ x1 - b) / np.linalg.norm(b) < 1e-12

@@ -197,3 +197,49 @@ def test_diagonal_groups_schedule():
     finally:
         whole.finalize()
         split.finalize()
+
+
+def test_factor_file_round_trip(tmp_path):
+    """Factor files (PanguLU's packed block format behind a small header): values written from one handle come back
+    bit for bit in another handle of the same matrix; the file is parsed here independently from the layout description."""
+    import struct
+
+    from pangulu_b200 import PanguLU, matrices
+
+    A = matrices.poisson3d(7)
+    nb = 24
+    s = PanguLU(A, nb=nb, host_only=True)
+    rng = np.random.default_rng(9)
+    vals = []
+    for b in s.blocks(copy=False):
+        b.value[:] = rng.uniform(-1, 1, b.value.shape)
+        vals.append(b.value.copy())
+    path = tmp_path / "factors.pglu"
+    nbytes = s.save_factors(path)
+    assert nbytes == os.path.getsize(path)
+    # independent parse: header, then one packed block after the other
+    raw = open(path, "rb").read()
+    magic, version, vtype, szv, fnb, n, bl, nblocks = struct.unpack_from("<8sIIIIIIQ", raw, 0)
+    assert magic == b"PGLUF01\x00" and version == 1 and vtype == 0 and szv == 8 and fnb == nb and n == A.shape[0] and nblocks == len(vals)
+    off = struct.calcsize("<8sIIIIIIQ") + n * (3 * 4 + 2 * 8)
+    for b, v in zip(s.blocks(copy=True), vals):
+        nnz, brow, bcol, is_upper = struct.unpack_from("<QIII", raw, off)
+        assert (nnz, brow, bcol) == (len(v), b.brow, b.bcol)
+        off += 32
+        assert np.array_equal(np.frombuffer(raw, np.float64, nnz, off), v)
+        off += 8 * nnz
+        assert np.array_equal(np.frombuffer(raw, np.uint32, nb + 1, off), b.colptr)
+        off += 4 * (nb + 1)
+        assert np.array_equal(np.frombuffer(raw, np.uint16, nnz, off), b.rowidx)
+        off += 2 * nnz
+        off += (8 - (4 * (nb + 1) + 2 * nnz) % 8) % 8
+        if brow > bcol:
+            assert np.array_equal(np.frombuffer(raw, np.uint32, nnz, off), b.csr2csc)
+            off += 4 * nnz + 4 * (nb + 1) + 2 * nnz
+            off += (8 - (4 * nnz + 4 * (nb + 1) + 2 * nnz) % 8) % 8
+    assert off == len(raw)
+    t = PanguLU(A, nb=nb, host_only=True)
+    assert t.load_factors(path) == len(vals)
+    for b, v in zip(t.blocks(copy=True), vals):
+        assert np.array_equal(b.value, v)
+    s.finalize(); t.finalize()
