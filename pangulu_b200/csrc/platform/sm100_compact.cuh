@@ -336,24 +336,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         mc = min(tm, max(0, MT - mi * tm));
         nc = min(tn, max(0, NT - ni * tn));
     };
-    // The row / column indices of the NEXT run's register tile are fetched from global memory while the current pair is
-    // multiplied (pre_for = index in the batch of the pair they belong to): a run then starts without an L2 round trip.
-    int pre_for = -1;
-    u16 pre_row = 0xffff, pre_col = 0xffff;
-    auto prefetch_run = [&](const CtPairSm& e, int pl) {
-        if constexpr (kDouble)
-        {
-            int mb, nbs, mc, nc;
-            grid_of(e.m, e.nt, mb, nbs, mc, nc);
-            const int r = mb + lane, c = nbs + lane;
-            const bool act = mc > 0 && nc > 0;
-            pre_row = (act && lane < mc * 8 && r < e.m) ? e.rows[r] : (u16)0xffff;
-            pre_col = (act && lane < nc * 8 && c < e.nt) ? e.cols[c] : (u16)0xffff;
-            pre_for = pl;
-        }
-    };
     // a new run: warp grid, this warp's piece, the row / column lists of its register tile
-    auto begin_run = [&](const CtPairSm& e, int pl) {
+    auto begin_run = [&](const CtPairSm& e) {
         cur_m = e.m; cur_nt = e.nt; cur_ld = e.ld;
         if constexpr (kDouble)
         {
@@ -364,14 +348,10 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             active = mtc > 0 && ntc > 0;
             if (active)
             {
-                u16 r16, c16;
-                if (pre_for == pl) { r16 = pre_row; c16 = pre_col; }
-                else
-                {
-                    const int r = m_base + lane, c = n_base + lane;
-                    r16 = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
-                    c16 = (lane < ntc * 8 && c < cur_nt) ? e.cols[c] : (u16)0xffff;
-                }
+                // (prefetching these two index loads during the previous pair was measured: no gain)
+                const int r = m_base + lane, c = n_base + lane;
+                const u16 r16 = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
+                const u16 c16 = (lane < ntc * 8 && c < cur_nt) ? e.cols[c] : (u16)0xffff;
                 wrow[lane] = r16;
                 u16 v = 0xffff;
                 if (c16 != 0xffff) { const unsigned char rk = crank[c16]; if (rk != 0xff) v = rk; }
@@ -381,7 +361,6 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         }
         else
         {
-            (void)pl;
             active = (cur_m > tx) && (ty * CPT < cur_nt);
 #pragma unroll
             for (int i2 = 0; i2 < 8; ++i2)
@@ -490,7 +469,6 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         // look-ahead nst-2, not nst-1: the slot a new item overwrites was released one full item earlier, so the producer
         // (a lane of a warp that also computes) rarely waits for the slowest warp of the item just consumed
         const int LA = nst > 2 ? nst - 2 : 1;
-        pre_for = -1;   // (pair indices are per batch)
 
         // producer step: bulk copies of item i into its slot
         auto produce = [&](int i) {
@@ -533,14 +511,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 if (have_run) flush();
                 lap(4);
                 have_run = true;
-                begin_run(e, pl);
+                begin_run(e);
                 lap(5);
-            }
-            // next run of this batch: start its index loads now
-            {
-                int nx = pl + 1;
-                while (nx < npb && (pc[nx].kmask & 0xffffu) == 0) ++nx;
-                if (nx < npb && (pc[nx].kmask & PSM_CT_RUNSTART)) prefetch_run(pc[nx], nx);
             }
             const bool warp_active = __any_sync(PSM_FULL, active);
             for (int j = 0; j < cnt; ++j, ++ci)
