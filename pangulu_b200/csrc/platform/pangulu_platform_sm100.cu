@@ -1985,20 +1985,28 @@ double pangulu_sm100_plan_stat(pangulu_sm100_plan* pl, const char* key)
 {
     if (!pl || !key) return -1;
     // "ct_prof_on<n>": profile the compact tile tasks with at least n operand pairs (library built with -DPSM_CT_PROFILE)
+    if (!strncmp(key, "ct_prof_max", 11))   // ... and at most n pairs ("ct_prof_max<n>", after "ct_prof_on<n>")
+    {
+        int mx = key[11] ? atoi(key + 11) : 0x7fffffff;
+        CK(cudaMemcpyToSymbol(g_ct_prof_max, &mx, sizeof mx));
+        return 0;
+    }
     if (!strncmp(key, "ct_prof_on", 10))
     {
         int on = key[10] ? atoi(key + 10) : 1;
+        const int mx = 0x7fffffff;
         CK(cudaMemcpyToSymbol(g_ct_prof_on, &on, sizeof on));
-        unsigned long long z[20] = {0};
+        CK(cudaMemcpyToSymbol(g_ct_prof_max, &mx, sizeof mx));
+        unsigned long long z[32] = {0};
         CK(cudaMemcpyToSymbol(g_ct_prof, z, sizeof z));
         return 0;
     }
     if (!strncmp(key, "ct_prof", 7) && key[7] >= '0' && key[7] <= '9')
     {
-        unsigned long long v[20];
+        unsigned long long v[32];
         CK(cudaMemcpyFromSymbol(v, g_ct_prof, sizeof v));
         const int k = atoi(key + 7);
-        return k < 20 ? (double)v[k] : -1.0;
+        return k < 32 ? (double)v[k] : -1.0;
     }
     if (!strcmp(key, "ct_tasks")) return pl->stat_ct_tasks;
     if (!strcmp(key, "ct_pairtiles")) return pl->stat_ct_pairtiles;

@@ -101,7 +101,8 @@ struct CtLayout
     static constexpr size_t item_off = pc_off + pc_bytes;
     static constexpr size_t rank_off = item_off + (size_t)PSM_CT_BATCH * 16 * 4;
     static constexpr size_t map_off = rank_off + 256 + 2 * TN;          // per warp: 32 row + 32 column indices of its register tile
-    static constexpr size_t total = map_off + 16 * 64 * 2 + 64;
+    static constexpr size_t eptr_off = map_off + 16 * 64 * 2 + 64;     // [nb + 1] destination column pointers of the tile's range (epilogue)
+    static constexpr size_t total = eptr_off + 4 * 260;
 };
 
 struct CtPairSm   // one staged operand pair (48 bytes)
@@ -157,13 +158,14 @@ __device__ __forceinline__ void ct_chunk_n(int ntc, double* racc, const double* 
 
 // Barrier state of a CTA that runs many compact-tile tasks (persistent executor): the mbarriers live in static shared
 // memory (other task kinds reuse the dynamic part), are initialised once, and every wait flips the barrier's bit.
-struct CtState { u32 full_bits = 0, empty_bits = 0; bool armed = false; };
+struct CtState { u32 full_bits = 0, empty_bits = 0, flush_bit = 0; bool armed = false; };
 
 // optional phase profile of the compact tile routine (warp 0 lane 0 of every CTA, clock64): prologue, staging, wait for
 // operands, compute, flush, pair setup, epilogue, produce
 __device__ int g_ct_gmax = 4, g_ct_minst = 2;   // ring policy of the compact tile routine (options "ct_gmax", "ct_minst")
-__device__ unsigned long long g_ct_prof[20];   // [0,10): thread 0;  [10,20): the producer thread
+__device__ unsigned long long g_ct_prof[32];   // [0,10): thread 0;  [10,20): the producer thread;  [20,28): compact panel routine, thread 0
 __device__ int g_ct_prof_on;
+__device__ int g_ct_prof_max = 0x7fffffff;     // ... and at most this many pairs
 
 // One CTA, one tile of the destination: the block columns [clo, chi).  The host cuts the tiles so that neither the
 // destination nor any B operand queued for it has more than TN NON-EMPTY columns in the range (compact column tiles:
@@ -189,7 +191,9 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     constexpr int CPT = TN / 16;  // FMA path: columns per thread
     T* acc = reinterpret_cast<T*>(smem_raw);
     unsigned char* ring = smem_raw + Lay::acc_bytes;
-    __shared__ __align__(8) unsigned long long bars[2 * NSLOT];  // [0,NSLOT) full, [NSLOT,2*NSLOT) empty
+    __shared__ __align__(8) unsigned long long bars[2 * NSLOT + 1];  // [0,NSLOT) full, [NSLOT,2*NSLOT) empty, [2*NSLOT] flush hand-over
+    unsigned long long* fbar = bars + 2 * NSLOT;
+    u32* eptr = reinterpret_cast<u32*>(smem_raw + Lay::eptr_off);
     CtPairSm* pc = reinterpret_cast<CtPairSm*>(smem_raw + Lay::pc_off);
     u32* items = reinterpret_cast<u32*>(smem_raw + Lay::item_off);  // (pair_in_batch << 16) | mask of the item's k-chunks (up to 4)
     unsigned char* crank = smem_raw + Lay::rank_off;                // [nb]: position of a column inside this tile, 0xff otherwise
@@ -205,7 +209,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     // phase profile: compiled in only with -DPSM_CT_PROFILE (the ten 64-bit counters cost 20 registers per thread)
 #ifdef PSM_CT_PROFILE
     // g_ct_prof_on = n: profile the tasks with at least n operand pairs (thread 0 and the producer thread)
-    const bool prof = g_ct_prof_on != 0 && (tid == 0 || tid == PTID) && (int)(D.pair_end - D.pair_begin) >= g_ct_prof_on;
+    const bool prof = g_ct_prof_on != 0 && (tid == 0 || tid == PTID) && (int)(D.pair_end - D.pair_begin) >= g_ct_prof_on &&
+                      (int)(D.pair_end - D.pair_begin) <= g_ct_prof_max;
     long long pt = prof ? clock64() : 0;
     unsigned long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     auto lap = [&](int k) { if (prof) { const long long now = clock64(); pacc[k] += (unsigned long long)(now - pt); pt = now; } };
@@ -218,17 +223,23 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         bool ne = false;
         if (tid >= clo && tid < chi)
         {
-            ne = D.c.ptr[tid + 1] > col_begin(D.c.ptr, tid);
+            // the pointers of the range's columns stay in shared memory: the epilogue walks the range's entries as one flat list
+            const u32 b = col_begin(D.c.ptr, tid), e = D.c.ptr[tid + 1];
+            eptr[tid - clo] = b;
+            if (tid == chi - 1) eptr[chi - clo] = e;
+            ne = e > b;
             if (diag) ne = ne || D.u.ptr[tid + 1] > col_begin(D.u.ptr, tid);
         }
         const unsigned bal = __ballot_sync(PSM_FULL, ne);
         if (tid < 256 && lane == 0) s_wcnt[warp] = __popc(bal);
         for (int i = tid; i < TN * LDC; i += 512) acc[i] = zero<T>();
-        if (!st.armed)
+        const bool arm = !st.armed;
+        if (arm)
         {
             if (tid == 0)
             {
                 for (int s = 0; s < NSLOT; ++s) { mbar_init(bars + s, 1); mbar_init(bars + NSLOT + s, 16); }
+                mbar_init(fbar, 16);
                 asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             }
             st.armed = true;
@@ -239,6 +250,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         // before the async-proxy reads of the bulk copies (cross-proxy fence, all state spaces).
         asm volatile("fence.proxy.async;" ::: "memory");
         __syncthreads();
+        if (arm && lane == 0) mbar_arrive(fbar);   // phase 0 of the flush hand-over = "no flush before the first one"
         if (tid < 256)
         {
             int before = 0;
@@ -272,15 +284,29 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     // staging warp: maps of the last pair with work, carried from batch to batch
     const u16 *carry_rows = nullptr, *carry_cols = nullptr;
 
+    u32 flush_bit = st.flush_bit;
+    u32 pend_rc = 0xffffffffu;   // DMMA path: this lane's entry of the run's row map (low half) and column map (high half)
     auto flush = [&]() {
         // registers -> accumulator tile in full row coordinates.  Which warp owns an element of the tile depends on the
-        // run's compaction and warp grid, and warps drift apart by up to nst-1 items: the barrier keeps the adds of
-        // consecutive runs apart (every warp passes here once per run, with or without work).
-        __syncthreads();
+        // run's compaction and warp grid, so the adds of consecutive runs must not overlap.  A SPLIT hand-over instead of
+        // a block barrier: a warp starts the adds of run i once every warp has ARRIVED after its adds of run i-1 -- which
+        // happened a whole run of tensor work ago -- so no warp (in particular not the one that also issues the bulk
+        // copies) holds the others up.  Every warp passes here once per run, with or without work.
+        mbar_wait(fbar, flush_bit);
+        flush_bit ^= 1u;
         if constexpr (kDouble)
         {
             if (active)
             {
+                // the run's maps were loaded when the run began (the loads were in flight during its tensor work)
+                {
+                    const u32 c16 = pend_rc >> 16;
+                    u16 v = 0xffff;
+                    if (c16 != 0xffffu) { const unsigned char rk = crank[c16]; if (rk != 0xff) v = rk; }
+                    wrow[lane] = (u16)(pend_rc & 0xffffu);
+                    wcol[lane] = v;
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt)
                 {
@@ -314,6 +340,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                     v = zero<T>();
                 }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(fbar);
     };
     // warp grid gm x gn (16 warps) of a run by its tile counts: fewest tensor instructions on the busiest warp, then fewest
     // fragment loads; at most 4 x 4 tiles of 8 x 8 per warp.  The row groups map onto the four SM sub-partitions (warp % 4),
@@ -346,18 +374,15 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             mtc = __popc(__ballot_sync(PSM_FULL, lane < mtc));
             ntc = __popc(__ballot_sync(PSM_FULL, lane < ntc));
             active = mtc > 0 && ntc > 0;
+            pend_rc = 0xffffffffu;
             if (active)
             {
-                // (prefetching these two index loads during the previous pair was measured: no gain)
+                // issued here, consumed by the run's flush: the two L2 round trips overlap the run's tensor work
                 const int r = m_base + lane, c = n_base + lane;
-                const u16 r16 = (lane < mtc * 8 && r < cur_m) ? e.rows[r] : (u16)0xffff;
-                const u16 c16 = (lane < ntc * 8 && c < cur_nt) ? e.cols[c] : (u16)0xffff;
-                wrow[lane] = r16;
-                u16 v = 0xffff;
-                if (c16 != 0xffff) { const unsigned char rk = crank[c16]; if (rk != 0xff) v = rk; }
-                wcol[lane] = v;
+                const u32 r16 = (lane < mtc * 8 && r < cur_m) ? (u32)e.rows[r] : 0xffffu;
+                const u32 c16 = (lane < ntc * 8 && c < cur_nt) ? (u32)e.cols[c] : 0xffffu;
+                pend_rc = r16 | (c16 << 16);
             }
-            __syncwarp();
         }
         else
         {
@@ -479,16 +504,30 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             const u32 it = items[i];
             const CtPairSm& e = pc[it >> 16];
             u32 m = it & 0xffffu;
-            unsigned char* sb = ring + (size_t)s * slot_bytes;
+            // slot image: the item's A chunks, then its B chunks.  Consecutive k-chunks are contiguous in the A copy, and in
+            // the B copy when the tile covers all of the operand's columns: one bulk copy per RUN of chunks (a copy costs
+            // ~110 issue cycles whatever its size, profiles/r02_bulk_issue_microbench.txt).
             const u32 abytes = (u32)(KC * e.ld * sizeof(T)), bbytes = (u32)(e.nt * BLD * sizeof(T));
-            mbar_expect_tx(bars + s, (u32)__popc(m) * (abytes + bbytes));
+            const u32 nchk = (u32)__popc(m);
+            unsigned char* sa = ring + (size_t)s * slot_bytes;
+            unsigned char* sbb = sa + nchk * abytes;
+            const bool bwhole = e.nt == e.nprime;
+            mbar_expect_tx(bars + s, nchk * (abytes + bbytes));
             while (m)
             {
                 const int ch = __ffs(m) - 1;
-                m &= m - 1;
-                bulk_g2s(sb, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, abytes, bars + s);
-                bulk_g2s(sb + abytes, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, bbytes, bars + s);
-                sb += abytes + bbytes;
+                const int r = __ffs(~(m >> ch)) - 1;   // chunks ch .. ch + r - 1 are all present
+                m &= ~(((1u << r) - 1u) << ch);
+                bulk_g2s(sa, reinterpret_cast<const T*>(e.a_dense) + (size_t)ch * KC * e.ld, (u32)r * abytes, bars + s);
+                sa += (u32)r * abytes;
+                if (bwhole)
+                {
+                    bulk_g2s(sbb, reinterpret_cast<const T*>(e.b_dense) + (size_t)ch * e.nprime * BLD, (u32)r * bbytes, bars + s);
+                    sbb += (u32)r * bbytes;
+                }
+                else
+                    for (int q = 0; q < r; ++q, sbb += bbytes)
+                        bulk_g2s(sbb, reinterpret_cast<const T*>(e.b_dense) + (size_t)(ch + q) * e.nprime * BLD, bbytes, bars + s);
             }
             lap(9);
         };
@@ -527,8 +566,8 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                 if (warp_active)
                   for (int q = 0; q < nch; ++q)
                   {
-                    const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes) + (size_t)q * (KC * cur_ld + cur_nt * BLD);
-                    const T* Bs = As + KC * cur_ld;
+                    const T* As = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes) + (size_t)q * (KC * cur_ld);
+                    const T* Bs = reinterpret_cast<const T*>(ring + (size_t)s * slot_bytes) + (size_t)nch * (KC * cur_ld) + (size_t)q * (cur_nt * BLD);
                     if constexpr (kDouble)
                     {
                         const double* Ap = As + lk * cur_ld + m_base + lr;
@@ -582,19 +621,42 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     if (have_run) flush();
     st.full_bits = full_bits;
     st.empty_bits = empty_bits;
+    st.flush_bit = flush_bit;
     lap(4);
 
     // ---- epilogue: accumulator tile -> destination pattern (other CTAs may update the same block: reductions)
     __syncthreads();
-    for (int jj = warp; jj < ncol; jj += 16)
     {
-        const int j = ccols[jj];
-        const u32 e0 = col_begin(D.c.ptr, j), e1 = D.c.ptr[j + 1];
-        const T* Cj = acc + jj * LDC;
-        for (u32 e = e0 + lane; e < e1; e += PSM_WARP)
+        // The entries of the columns [clo, chi) are ONE contiguous piece of the CSC arrays: a flat loop with four independent
+        // index loads in flight per thread (a loop over columns is a chain of dependent L2 round trips -- ~15 us per task,
+        // which is all a small task costs); the column of an entry by bisection over the staged pointers.
+        const int nrange = chi - clo;
+        const u32 e_lo = eptr[0], e_hi = eptr[nrange];
+        for (u32 base = e_lo + tid; base < e_hi; base += 4 * 512)
         {
-            const T v = Cj[D.c.idx[e]];
-            if (!is_zero(v)) red_sub(&D.c.val[e], v);
+            u16 ri[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const u32 e = base + u * 512;
+                ri[u] = e < e_hi ? D.c.idx[e] : (u16)0;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+            {
+                const u32 e = base + u * 512;
+                if (e < e_hi)
+                {
+                    int lo = 0, hi = nrange;   // largest column with eptr[column] <= e (skips empty columns)
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (eptr[mid] <= e) lo = mid; else hi = mid; }
+                    const unsigned char rk = crank[clo + lo];
+                    if (rk != 0xff)
+                    {
+                        const T v = acc[(int)rk * LDC + ri[u]];
+                        if (!is_zero(v)) red_sub(&D.c.val[e], v);
+                    }
+                }
+            }
         }
     }
     if (diag)
@@ -726,6 +788,15 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     const u32 kmask = Dn.kmask;
     const int nrows = min(R, (int)Dn.cnt - r0);   // compact rows / columns of this slice
     const Blk<T> B = Q.b;
+#ifdef PSM_CT_PROFILE
+    // phases (thread 0): 0 clear + staging, 1 gather, 2 wait for the triangular factor, 3 tensor update, 4 substitution, 5 scatter, 6 dense copy
+    const bool cprof = g_ct_prof_on != 0 && tid == 0;
+    long long cpt = cprof ? clock64() : 0;
+    unsigned long long cpacc[7] = {0, 0, 0, 0, 0, 0, 0};
+    auto clap = [&](int k) { if (cprof) { const long long now = clock64(); cpacc[k] += (unsigned long long)(now - cpt); cpt = now; } };
+#else
+    auto clap = [](int) {};
+#endif
 
     if (!st.armed)
     {
@@ -868,8 +939,10 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
             }
         }
     };
+    clap(0);
     sweep(0);
     __syncthreads();
+    clap(1);
 
     const int lr = lane / 4, lk = lane % 4, lc = (lane % 4) * 2;
     const int mtile = warp & 7, ntile = warp >> 3;
@@ -881,6 +954,7 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
         if (tid == 0 && Jnext >= 0) issue(Jnext, par ^ 1);   // prefetch the next column block
         mbar_wait(cbars + par, (bits >> par) & 1u);
         bits ^= 1u << par;
+        clap(2);
         const T* Tb = reinterpret_cast<const T*>(tb0 + (size_t)par * Lay::tbuf_bytes);
         // ---- X[:, J] -= X[:, <J] Tm(<J, J)
         u32 need = 0;
@@ -931,6 +1005,7 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
             }
             __syncthreads();
         }
+        clap(3);
         // ---- 16-column substitution against the diagonal sub-block, one thread per row
         if (tid < R)
         {
@@ -952,6 +1027,7 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
             for (int c = 0; c < 16; ++c) X[(Jcur * 16 + c) * LDX + tid] = x[c];
         }
         __syncthreads();
+        clap(4);
         Jcur = Jnext;
         par ^= 1;
     }
@@ -959,6 +1035,7 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
 
     // ---- write back: CSC values and the compact dense copy
     sweep(1);
+    clap(5);
     if (gessm)
     {
         // dense copy (B-operand layout): (k, c') at ((k/16) n' + c') 20 + k%16 -- 16 consecutive k are contiguous
@@ -979,6 +1056,11 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
         }
     }
     __syncthreads();
+    clap(6);
+#ifdef PSM_CT_PROFILE
+    if (cprof)
+        for (int k = 0; k < 7; ++k) atomicAdd(&g_ct_prof[20 + k], cpacc[k]);
+#endif
 }
 
 template <class T>

@@ -8,4 +8,7 @@ mkdir -p $O
 echo "pytest rc=$?" >> $O/pytest.log
 ( timeout 300 scripts/micro/ctile_bench ) > $O/ctile_bench.txt 2>&1
 ( time timeout 900 python scripts/trace_mega.py --size 100 ) > $O/trace100.txt 2>&1
+( time PANGULU_SM100_LIB_DIR=$PWD/pangulu_b200/lib_prof CT_PROF=1 CT_PROF_MAX=8 timeout 900 python scripts/trace_mega.py --size 100 ) > $O/trace100_prof_small.txt 2>&1
+( time PANGULU_SM100_LIB_DIR=$PWD/pangulu_b200/lib_prof CT_PROF=64 timeout 900 python scripts/trace_mega.py --size 100 ) > $O/trace100_prof_heavy.txt 2>&1
+grep "phases" $O/trace100_prof_small.txt $O/trace100_prof_heavy.txt
 tail -4 $O/pytest.log; cat $O/debug_cr64_n3000.txt $O/debug_cr64_n1200.txt | cut -c1-400; cat $O/ctile_bench.txt; head -12 $O/trace100.txt

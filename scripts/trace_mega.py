@@ -14,7 +14,9 @@ for kv in a.opt:
     k, v = kv.split("="); assert L.pangulu_sm100_set_option(k.encode(), int(v)) == 0
 s = PanguLU(matrices.poisson3d(a.size), nb=a.nb, mode=1, schedule=a.schedule, lookahead=a.lookahead)
 s.gstrf(); s.reset_values(True)
-if os.environ.get('CT_PROF'): s.info('plan_ct_prof_on' + os.environ['CT_PROF'])
+if os.environ.get('CT_PROF'):
+    s.info('plan_ct_prof_on' + os.environ['CT_PROF'])
+    if os.environ.get('CT_PROF_MAX'): s.info('plan_ct_prof_max' + os.environ['CT_PROF_MAX'])
 t = s.gstrf()
 n = L.pangulu_sm100_driver_trace(s._h, None, 0)
 buf = np.zeros((n, 4), dtype=np.uint64)
@@ -43,6 +45,10 @@ if os.environ.get('CT_PROF'):
         tot = sum(v)
         if tot > 0:
             print(f"compact tile phases, tasks with >= {os.environ['CT_PROF']} pairs ({who}, cycles): " + "  ".join(f"{n} {x/tot*100:.1f}%" for n, x in zip(names7, v)) + f"  total {tot/1.965e9:.1f} CTA-s")
+    v = [s.info("plan_ct_prof%d" % (20 + k)) for k in range(7)]
+    if sum(v) > 0:
+        cn = ["clear+staging", "gather", "wait_factor", "tensor_update", "substitution", "scatter", "dense_copy"]
+        print("compact panel phases (thread 0, cycles): " + "  ".join(f"{n} {x/sum(v)*100:.1f}%" for n, x in zip(cn, v)) + f"  total {sum(v)/1.965e9:.1f} CTA-s")
 print(f"flop {s.info('flop'):.4e}  -> {s.info('flop')/t/1e9:.1f} GFLOP/s")
 for k in (0, 6):
     m = kind == k

@@ -72,3 +72,38 @@ def test_reference_gstrf_runs_the_plan_path(name, make, nb):
     assert worst <= TOL["r64"], worst
     assert float(gpu["resid"]) <= max(4 * float(cpu["resid"]), 1e-15)
     assert gpu["plan_times"][2] > 0, "pangulu_gstrf did not take the plan path"
+
+
+def test_mc64_build_of_the_reference_on_the_plan_path():
+    """BASELINE's "MC64+METIS" configuration: the reference compiled with its own -DPANGULU_MC64 (scaling + row matching in
+    pangulu_init, src/pangulu_reordering.c:149-680) on the CPU platform and on this module's plan path; the input is a
+    row- and column-scaled Poisson matrix, so the scaling vectors are not trivial.  Scaling, permutations and structure
+    bit-exact (the same host code computes them), values and residual as everywhere."""
+    import scipy.sparse as sp
+
+    from oracle.ref import ref_available
+    from oracle.ref_run import run_reference, unflatten
+
+    if not (ref_available("r64", flavour="planmc64") and ref_available("r64", flavour="cpumc64")):
+        pytest.skip("oracle/_ref MC64 builds not present on this box")
+    A0 = matrices.poisson3d(16)
+    n = A0.shape[0]
+    rng = np.random.default_rng(3)
+    A = sp.csc_matrix(sp.diags(10.0 ** rng.uniform(-1, 1, n)) @ A0 @ sp.diags(10.0 ** rng.uniform(-1, 1, n)))
+    A.sort_indices()
+    nb = 64
+    cpu = run_reference(A, nb, flavour="cpumc64")
+    gpu = run_reference(A, nb, flavour="planmc64")
+    assert not np.allclose(cpu["row_scale"], 1.0), "MC64 scaling did not run"
+    for k in ("row_perm", "col_perm", "metis_perm", "row_scale", "col_scale"):
+        assert np.array_equal(cpu[k], gpu[k]), k
+    want, got = unflatten(cpu, "post_", nb), unflatten(gpu, "post_", nb)
+    assert len(want) == len(got)
+    worst = 0.0
+    for g, w in zip(got, want):
+        assert (g.brow, g.bcol, g.is_upper) == (w.brow, w.bcol, w.is_upper)
+        assert np.array_equal(g.colptr, w.colptr) and np.array_equal(g.rowidx, w.rowidx)
+        worst = max(worst, rel_err(g.value, w.value))
+    assert worst <= TOL["r64"], worst
+    assert float(gpu["resid"]) <= max(4 * float(cpu["resid"]), 1e-15)
+    assert gpu["plan_times"][2] > 0, "pangulu_gstrf did not take the plan path"
