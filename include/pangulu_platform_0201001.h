@@ -131,6 +131,18 @@ void pangulu_sm100_download_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, p
 /* ... and host -> device (re-factorisation with new values on an unchanged pattern). */
 void pangulu_sm100_upload_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t **slots);
 
+/* Preprocessing on the device.
+ * scatter_values: clear clear_bytes bytes at d_region (0: leave it), then region[d_dst[i]] = d_src[i] (* d_scale[i] when
+ *   d_scale is not NULL) for i < n; entries with d_dst[i] == ~0 are skipped.  This is the value scatter of
+ *   src/pangulu_conversion.c:241-350 with the positions precomputed once per pattern; all pointers are device pointers,
+ *   values are calculate_type.
+ * mirror_patterns: rebuild d_rowpointer / d_columnindex / d_idx_of_csc_value_for_csr of n strictly-lower blocks from their
+ *   d_columnpointer / d_rowindex (pangulu_transpose_struct_with_valueidx_inblock, src/pangulu_utils.c:479-511); bit-identical
+ *   to the host routine.  Returns after the device work is complete. */
+void pangulu_sm100_scatter_values(void *d_region, size_t clear_bytes, const unsigned long long *d_dst, const void *d_src, const void *d_scale,
+                                  unsigned long long n);
+void pangulu_sm100_mirror_patterns(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t **slots);
+
 /* Static plan: the whole task graph of one rank, translated once into device-resident descriptors.
  * waves[w] .. waves[w+1] index tasks[]; waves execute in order, tasks inside a wave are independent
  * except SSSSM tasks sharing opdst (combined).  plan_execute only enqueues; PSM(synchronize) completes it. */

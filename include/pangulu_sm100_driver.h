@@ -80,6 +80,14 @@ const pangulu_task_t *pangulu_sm100_driver_tasks(void *handle, const pangulu_uin
 void pangulu_sm100_driver_set_mode(void *handle, int mode);
 /* put the values of A back into the host block buffers (and the device copy) so gstrf can run again */
 void pangulu_sm100_driver_reset_values(void *handle, int also_device);
+/* Preprocessing on the device.
+ * update_values: the matrix again in the CSC arrays given to pangulu_init -- same pattern, new values; nnz(A) values travel to
+ *   the device, the block value region is cleared there and the values are scattered by a kernel (first call: the positions are
+ *   computed once).  The host copy of the reordered matrix follows; the host block buffers do not.  Returns seconds.
+ * device_mirrors: rebuild the CSR mirrors (rowpointer / columnindex / idx_of_csc_value_for_csr) of the owned strictly-lower
+ *   blocks on the device; returns the number of bytes in which the device index region differs from the host-built one. */
+double pangulu_sm100_driver_update_values(void *handle, const sparse_pointer_t *colptr, const sparse_index_t *rowidx, const sparse_value_t *val);
+long long pangulu_sm100_driver_device_mirrors(void *handle, int clear_first);
 /* resident mode: enqueue the whole factorisation on the module's stream (pangulu_sm100_stream()) without
  * synchronising; <id>_synchronize() or a stream event completes it */
 void pangulu_sm100_driver_gstrf_enqueue(void *handle);

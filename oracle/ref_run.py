@@ -85,7 +85,7 @@ def main(argv=None):
         _flatten(f.blocks(), "pre_", out)
     t = f.gstrf()
     out["t_gstrf"] = t
-    if a.flavour == "plan":
+    if a.flavour.startswith("plan"):
         # the overlay's pangulu_gstrf ran this module's plan path: its phase times, and a second (warm: schedule and plan cached)
         # factorisation after the values of A were put back into PanguLU's blocks
         import ctypes as C

@@ -14,6 +14,7 @@
 //      plan on values already in HBM and synchronises (bench.py's "value").
 //   2  host buffers + resident plan: upload the value region, run the plan, download the factors (bench.py's "e2e").
 #include <algorithm>
+#include <complex>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -65,6 +66,12 @@ struct Handle
     std::vector<void*> ipc_opened;
     bool wired = false;
     std::map<std::string, double> times;
+    // preprocessing on the device (pangulu_sm100_driver_update_values): per entry of the caller's CSC arrays its position in the
+    // value region (device, u64; ~0 = held by another rank) and in A_reordered (host), built on the first call; staging for the values
+    unsigned long long* d_scatter_dst = nullptr;
+    T* d_scatter_src = nullptr;
+    std::vector<uint64_t> pos_in_reordered;
+    uint64_t scatter_nnz = 0, scatter_extra = 0;
 };
 
 void scatter_values(Handle* h);
@@ -339,6 +346,8 @@ void pangulu_finalize(void** pangulu_handle)
         for (eidx k = 0; k < h->B.block_length; ++k)
             if (h->sched.group_count.size() > k && h->sched.group_count[k] > 1 && h->B.slot_of_diag[k] >= 0)
                 pangulu_sm100_set_diag_groups(&h->B.slots[h->B.slot_of_diag[k]], 0, nullptr);
+    if (h->d_scatter_dst) PSM(free)(h->d_scatter_dst);
+    if (h->d_scatter_src) PSM(free)(h->d_scatter_src);
     free_blocks(h->B);
     delete h;
     *pangulu_handle = NULL;
@@ -460,6 +469,149 @@ void pangulu_sm100_driver_reset_values(void* handle, int also_device)
     scatter_values(h);
     if (also_device && !h->B.host_only) PSM(memcpy)(h->B.d_buf, h->B.h_buf, h->B.value_bytes, 0);
     h->factored = false;
+}
+
+// Value scatter on the device (reference: the host loops of src/pangulu_conversion.c:241-350).  The caller passes
+// the matrix again in the CSC arrays it gave pangulu_init -- same pattern, new values (a Newton or time-stepping loop).  The
+// first call computes where every entry lives in the block value region; every call then moves nnz(A) values to the
+// device (instead of nnz(L+U)), clears the region there and scatters.  Returns the seconds spent.
+double pangulu_sm100_driver_update_values(void* handle, const sparse_pointer_t* colptr, const sparse_index_t* rowidx, const sparse_value_t* val)
+{
+    Handle* h = (Handle*)handle;
+    BlockStore& B = h->B;
+    if (B.host_only)
+    {
+        fprintf(stderr, "[PanguLU ERROR] update_values needs the GPU (handle was created in host_only mode)\n");
+        exit(EXIT_FAILURE);
+    }
+    const double t0 = wall_seconds();
+    const eidx n = h->n;
+    const int nb = B.nb;
+    const uint64_t nnz = colptr[n];
+    const Csc& Ar = h->A_reordered;
+    if (!h->d_scatter_dst || h->scatter_nnz != nnz)
+    {
+        std::vector<unsigned long long> dst(nnz, ~0ull);
+        h->pos_in_reordered.assign(nnz, ~0ull);
+        auto find_in = [](const iidx* idx, iptr b, iptr e, iidx key) -> int64_t {
+            const iidx* it = std::lower_bound(idx + b, idx + e, key);
+            if (it == idx + e || *it != key) return -1;
+            return (int64_t)(it - idx);
+        };
+        long long bad = 0;
+#pragma omp parallel for schedule(dynamic, 1024) reduction(+ : bad)
+        for (int64_t c0 = 0; c0 < (int64_t)n; ++c0)
+        {
+            const eidx c = h->R.metis_perm[h->R.col_perm[c0]];
+            const eidx J = c / nb;
+            const iidx cl = (iidx)(c - J * nb);
+            for (uint64_t e = colptr[c0]; e < colptr[c0 + 1]; ++e)
+            {
+                const eidx r = h->R.metis_perm[h->R.row_perm[rowidx[e]]];
+                // position in the reordered matrix (factor check, reset_values)
+                {
+                    const eidx* b0 = Ar.idx.data() + Ar.ptr[c];
+                    const eidx* b1 = Ar.idx.data() + Ar.ptr[c + 1];
+                    const eidx* it = std::lower_bound(b0, b1, r);
+                    if (it == b1 || *it != r) { bad++; continue; }
+                    h->pos_in_reordered[e] = (uint64_t)(it - Ar.idx.data());
+                }
+                const eidx I = r / nb;
+                const iidx rl = (iidx)(r - I * nb);
+                const pangulu_storage_slot_t* sl = nullptr;
+                int64_t pos = -1;
+                if (I == J)
+                {
+                    const int64_t ds = B.slot_of_diag[J];
+                    if (ds < 0) continue;
+                    if (r == c) { sl = &B.slots[ds + 1]; pos = cl == 0 ? 0 : sl->columnpointer[cl]; }
+                    else if (r > c) { sl = &B.slots[ds]; pos = find_in(sl->rowindex, cl == 0 ? 0 : sl->columnpointer[cl], sl->columnpointer[cl + 1], rl); }
+                    else { sl = &B.slots[ds + 1]; pos = find_in(sl->rowindex, rl == 0 ? 0 : sl->columnpointer[rl], sl->columnpointer[rl + 1], cl); }
+                }
+                else
+                {
+                    const int64_t gid = B.find_block(I, J);
+                    if (gid < 0) { bad++; continue; }
+                    const int64_t si = B.slot_of_block[gid];
+                    if (si < 0) continue;
+                    sl = &B.slots[si];
+                    pos = find_in(sl->rowindex, cl == 0 ? 0 : sl->columnpointer[cl], sl->columnpointer[cl + 1], rl);
+                }
+                if (pos < 0) { bad++; continue; }
+                dst[e] = (unsigned long long)(((const char*)(sl->value + pos) - B.h_buf) / sizeof(T));
+            }
+        }
+        if (bad)
+        {
+            fprintf(stderr, "[PanguLU ERROR] update_values: %lld entries are not in the pattern the handle was built for\n", bad);
+            exit(EXIT_FAILURE);
+        }
+        // diagonal entries pangulu_init inserted (1e-8, src/pangulu_reordering.c:715-796) are not in the caller's arrays
+        std::vector<char> seen(Ar.ptr[n], 0);
+        for (uint64_t e = 0; e < nnz; ++e) seen[h->pos_in_reordered[e]] = 1;
+        std::vector<unsigned long long> extra_dst;
+        for (eidx c = 0; c < n; ++c)
+            for (eptr e = Ar.ptr[c]; e < Ar.ptr[c + 1]; ++e)
+                if (!seen[e] && Ar.idx[e] == c)
+                {
+                    const int64_t ds = B.slot_of_diag[c / nb];
+                    if (ds < 0) continue;
+                    const pangulu_storage_slot_t* sl = &B.slots[ds + 1];
+                    const iidx cl = (iidx)(c % nb);
+                    extra_dst.push_back((unsigned long long)(((const char*)(sl->value + (cl == 0 ? 0 : sl->columnpointer[cl])) - B.h_buf) / sizeof(T)));
+                }
+        h->scatter_extra = extra_dst.size();
+        dst.insert(dst.end(), extra_dst.begin(), extra_dst.end());
+        if (h->d_scatter_dst) PSM(free)(h->d_scatter_dst);
+        if (h->d_scatter_src) PSM(free)(h->d_scatter_src);
+        PSM(malloc)((void**)&h->d_scatter_dst, dst.size() * sizeof(unsigned long long));
+        PSM(malloc)((void**)&h->d_scatter_src, dst.size() * sizeof(T));
+        PSM(memcpy)(h->d_scatter_dst, dst.data(), dst.size() * sizeof(unsigned long long), 0);
+        std::vector<T> tail(h->scatter_extra, t_from_real(1e-8));
+        if (h->scatter_extra) PSM(memcpy)(h->d_scatter_src + nnz, tail.data(), tail.size() * sizeof(T), 0);
+        h->scatter_nnz = nnz;
+    }
+    // host copy of the reordered matrix (the factor check and reset_values read it)
+    {
+        const T* v = (const T*)val;
+        T* out = h->A_reordered.val.data();
+#pragma omp parallel for schedule(static)
+        for (int64_t e = 0; e < (int64_t)nnz; ++e) out[h->pos_in_reordered[e]] = v[e];
+    }
+    PSM(memcpy)(h->d_scatter_src, val, nnz * sizeof(T), 0);
+    pangulu_sm100_scatter_values(B.d_buf, B.value_bytes, h->d_scatter_dst, h->d_scatter_src, nullptr, nnz + h->scatter_extra);
+    PSM(synchronize)();
+    h->factored = false;
+    return wall_seconds() - t0;
+}
+
+// CSR mirrors of the owned strictly-lower blocks rebuilt ON THE DEVICE from their CSC patterns (reference:
+// pangulu_transpose_struct_with_valueidx_inblock, src/pangulu_utils.c:479-511).  clear_first = 1 overwrites the three device
+// arrays of every such block with 0xff first (they were uploaded from the host-built copies at init).  Returns the number of
+// bytes in which the device's index region then differs from the host-built one (0 = bit-identical).
+long long pangulu_sm100_driver_device_mirrors(void* handle, int clear_first)
+{
+    Handle* h = (Handle*)handle;
+    BlockStore& B = h->B;
+    if (B.host_only) return -1;
+    std::vector<pangulu_storage_slot_t*> lower;
+    for (pangulu_storage_slot_t& s : B.slots)
+        if (s.brow_pos > s.bcol_pos && s.d_rowpointer && s.d_idx_of_csc_value_for_csr) lower.push_back(&s);
+    if (clear_first)
+        for (pangulu_storage_slot_t* s : lower)
+        {
+            const size_t nnz = s->columnpointer[B.nb];
+            PSM(memset)(s->d_rowpointer, 0xff, sizeof(iptr) * (size_t)(B.nb + 1));
+            PSM(memset)(s->d_columnindex, 0xff, sizeof(iidx) * nnz);
+            PSM(memset)(s->d_idx_of_csc_value_for_csr, 0xff, sizeof(iptr) * nnz);
+        }
+    pangulu_sm100_mirror_patterns((pangulu_inblock_idx)B.nb, lower.size(), lower.data());
+    const size_t index_bytes = B.buf_bytes - B.value_bytes;
+    std::vector<char> got(index_bytes);
+    PSM(memcpy)(got.data(), B.d_buf + B.value_bytes, index_bytes, 1);
+    long long diff = 0;
+    for (size_t i = 0; i < index_bytes; ++i) diff += got[i] != B.h_buf[B.value_bytes + i];
+    return diff;
 }
 
 // resident mode only: enqueue the whole factorisation on the module's stream and return without
@@ -826,14 +978,17 @@ double pangulu_sm100_driver_factor_check(void* handle)
     const BlockStore& B = h->B;
     const int nb = B.nb;
     const size_t N = (size_t)B.block_length * nb;
-    std::vector<long double> ux(N, 0.0L), lux(N, 0.0L), ax(N, 0.0L);
 #ifdef PANGULU_COMPLEX
-    (void)ux; (void)lux; (void)ax;
-    return NAN;  // the real-valued check is enough for the parity gates; complex uses the solve residual
+    typedef std::complex<long double> acc_t;
+    auto wide = [](const T& v) { return acc_t((long double)v.re, (long double)v.im); };
 #else
+    typedef long double acc_t;
+    auto wide = [](const T& v) { return (long double)v; };
+#endif
+    std::vector<acc_t> ux(N, acc_t(0)), lux(N, acc_t(0)), ax(N, acc_t(0));
     const Csc& A = h->A_reordered;
     for (eidx c = 0; c < A.n; ++c)
-        for (eptr e = A.ptr[c]; e < A.ptr[c + 1]; ++e) ax[A.idx[e]] += (long double)A.val[e];
+        for (eptr e = A.ptr[c]; e < A.ptr[c + 1]; ++e) ax[A.idx[e]] += wide(A.val[e]);
     // U * 1
     for (const pangulu_storage_slot_t& s : B.slots)
     {
@@ -842,12 +997,12 @@ double pangulu_sm100_driver_factor_check(void* handle)
         if (s.brow_pos == s.bcol_pos && s.is_upper)
         {
             for (int r = 0; r < nb; ++r)
-                for (iptr e = s.columnpointer[r]; e < s.columnpointer[r + 1]; ++e) ux[r0 + r] += (long double)s.value[e];
+                for (iptr e = s.columnpointer[r]; e < s.columnpointer[r + 1]; ++e) ux[r0 + r] += wide(s.value[e]);
         }
         else if (s.brow_pos < s.bcol_pos)
         {
             for (int c = 0; c < nb; ++c)
-                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) ux[r0 + s.rowindex[e]] += (long double)s.value[e];
+                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) ux[r0 + s.rowindex[e]] += wide(s.value[e]);
         }
     }
     // L * (U 1), unit diagonal
@@ -859,17 +1014,16 @@ double pangulu_sm100_driver_factor_check(void* handle)
         if ((s.brow_pos == s.bcol_pos && !s.is_upper) || s.brow_pos > s.bcol_pos)
         {
             for (int c = 0; c < nb; ++c)
-                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) lux[r0 + s.rowindex[e]] += (long double)s.value[e] * ux[c0 + c];
+                for (iptr e = s.columnpointer[c]; e < s.columnpointer[c + 1]; ++e) lux[r0 + s.rowindex[e]] += wide(s.value[e]) * ux[c0 + c];
         }
     }
     long double num = 0, den = 0;
     for (eidx i = 0; i < A.n; ++i)
     {
-        num += (lux[i] - ax[i]) * (lux[i] - ax[i]);
-        den += ax[i] * ax[i];
+        num += std::norm(acc_t(lux[i] - ax[i]));
+        den += std::norm(acc_t(ax[i]));
     }
     return (double)std::sqrt((double)(num / den));
-#endif
 }
 
 }  // extern "C"

@@ -18,6 +18,7 @@
 
 #include "pangulu_platform_0201001.h"
 #include "sm100_kernels.cuh"
+#include "sm100_preprocess.cuh"
 
 // globals of the PanguLU core (src/pangulu.c:7-9); absent when the module is used stand-alone
 extern "C" {
@@ -34,9 +35,28 @@ typedef calculate_type T;
 #define PSM_STR2(x) #x
 #define PSM_STR(x) PSM_STR2(x)
 
+// Progress board of the persistent executor (option "progress" = 1): every CTA notes the task it holds in HOST-mapped
+// memory, which stays readable after a failed launch -- the dump names the tasks that never finished.
+int4* g_progress_host = nullptr;
+int g_progress_ctas = 0;
+void dump_progress()
+{
+    if (!g_progress_host) return;
+    static const char* kinds[] = {"tile", "sparse", "getrf_smem", "getrf_dense", "getrf_global", "panel", "ctile", "cpanel", "ddens"};
+    for (int b = 0; b < g_progress_ctas; ++b)
+    {
+        const int4 v = g_progress_host[b];
+        if (v.w == 2) continue;   // finished its last task
+        fprintf(stderr, "[PanguLU ERROR]   CTA %3d: task %d kind %s arg %d state %s\n", b, v.x, (v.y >= 0 && v.y < 9) ? kinds[v.y] : "?", v.z,
+                v.w == 0 ? "waiting for dependencies" : "running");
+
+    }
+}
+
 [[noreturn]] void fatal(const char* file, int line, const char* what, const char* detail)
 {
     fprintf(stderr, "[PanguLU ERROR] sm100 platform: %s%s%s at %s:%d\n", what, detail ? ": " : "", detail ? detail : "", file, line);
+    dump_progress();
     fflush(stderr);
     exit(EXIT_FAILURE);
 }
@@ -71,6 +91,7 @@ struct Options
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
     long long ct_gmax = 4, ct_minst = 2;  // compact tile ring policy: chunks per item (at most), items the ring must hold (at least)
+    long long progress = 0;     // persistent executor: per-CTA progress board in host-mapped memory, dumped when a launch fails (debugging aid)
     long long spin_timeout_ms = 30000;  // persistent executor: a dependency wait longer than this aborts the run with [PanguLU ERROR]
 };
 
@@ -1270,6 +1291,17 @@ void launch_mega(pangulu_sm100_plan* pl)
     if ((size_t)16 * pl->nb * sizeof(T) + 4096 > smem)
         fatal(__FILE__, __LINE__, "block size nb is too large for the persistent executor's per-warp shared-memory vectors; reduce init_options.nb or set option executor=0", nullptr);
     const int grid = g.sm_count;
+    mp.progress = nullptr;
+    if (g.opt.progress)
+    {
+        if (!g_progress_host)
+        {
+            CK(cudaHostAlloc((void**)&g_progress_host, sizeof(int4) * 1024, cudaHostAllocMapped));
+            g_progress_ctas = grid;
+        }
+        for (int b = 0; b < 1024; ++b) g_progress_host[b] = make_int4(-1, -1, 0, 2);
+        CK(cudaHostGetDevicePointer((void**)&mp.progress, g_progress_host, 0));
+    }
     {
         const unsigned long long lim = (unsigned long long)std::max<long long>(1, g.opt.spin_timeout_ms) * 1000000ull;
         const int zero_flag = 0;
@@ -1543,6 +1575,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "cpanel_block_threshold")) return &g.opt.cpanel_block_threshold;
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     if (!strcmp(key, "spin_timeout_ms")) return &g.opt.spin_timeout_ms;
+    if (!strcmp(key, "progress")) return &g.opt.progress;
     if (!strcmp(key, "ct_gmax")) return &g.opt.ct_gmax;
     if (!strcmp(key, "ct_minst")) return &g.opt.ct_minst;
     return nullptr;
@@ -1587,6 +1620,44 @@ void pangulu_sm100_upload_blocks(pangulu_inblock_idx nb, pangulu_uint64_t n, pan
     for (pangulu_uint64_t i = 0; i < n; ++i)
         CK(cudaMemcpyAsync(slots[i]->d_value, slots[i]->value, sizeof(T) * (size_t)slot_nnz(nb, slots[i]), cudaMemcpyHostToDevice, g.stream));
     g.launches[K_AUX] += (long long)n;
+}
+
+// ---- preprocessing on the device (sm100_preprocess.cuh; reference: src/pangulu_conversion.c:241-350, src/pangulu_utils.c:479-511)
+void pangulu_sm100_scatter_values(void* d_region, size_t clear_bytes, const unsigned long long* d_dst, const void* d_src, const void* d_scale,
+                                  unsigned long long n)
+{
+    ensure_ctx();
+    if (clear_bytes) CK(cudaMemsetAsync(d_region, 0, clear_bytes, g.stream));
+    if (!n) return;
+    const unsigned grid = (unsigned)std::min<unsigned long long>((n + 255) / 256, (unsigned long long)g.sm_count * 8);
+    scatter_values_kernel<T><<<grid, 256, 0, g.stream>>>((T*)d_region, d_dst, (const T*)d_src, (const T*)d_scale, n);
+    CK_LAST();
+    g.launches[K_AUX]++;
+}
+
+void pangulu_sm100_mirror_patterns(pangulu_inblock_idx nb, pangulu_uint64_t n, pangulu_storage_slot_t** slots)
+{
+    ensure_ctx();
+    if (!n) return;
+    const size_t smem = ((size_t)nb * ((nb + 31) / 32) + nb + 1) * sizeof(u32);
+    if (smem > (size_t)g.max_smem_optin)
+        fatal(__FILE__, __LINE__, "block size nb is too large for the device-side CSR mirror (occupancy bitmap in shared memory)", nullptr);
+    std::vector<MirrorTask> tasks((size_t)n);
+    for (pangulu_uint64_t i = 0; i < n; ++i)
+    {
+        const pangulu_storage_slot_t* s = slots[i];
+        tasks[i] = {(const u32*)s->d_columnpointer, (const u16*)s->d_rowindex, (u32*)s->d_rowpointer, (u16*)s->d_columnindex,
+                    (u32*)s->d_idx_of_csc_value_for_csr};
+    }
+    MirrorTask* d_tasks = nullptr;
+    CK(cudaMalloc(&d_tasks, tasks.size() * sizeof(MirrorTask)));
+    CK(cudaMemcpyAsync(d_tasks, tasks.data(), tasks.size() * sizeof(MirrorTask), cudaMemcpyHostToDevice, g.stream));
+    set_smem(csr_mirror_kernel, smem);
+    csr_mirror_kernel<<<(unsigned)n, 256, smem, g.stream>>>((int)nb, d_tasks);
+    CK_LAST();
+    CK(cudaStreamSynchronize(g.stream));   // (tasks[] is read by the copy above)
+    CK(cudaFree(d_tasks));
+    g.launches[K_AUX]++;
 }
 
 pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_uint64_t nwave, const pangulu_uint64_t* waves,
@@ -1665,6 +1736,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             if ((P.panel[i].kind & 0xff) == PANGULU_TASK_GESSM) dn.lt = true; else dn.u = true;
         }
         const size_t tri = (size_t)(nb / 16) * nb * PSM_CT_BLD;  // values per triangular copy
+        const size_t tri_u = tri + (size_t)nb;                   // U copies carry the nb pivot reciprocals behind them
         size_t total = 0;
         for (size_t gi = 0; gi < P.getrf_slot.size(); ++gi)
         {
@@ -1680,7 +1752,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             if (it->second.u)
             {
                 dd.u = (T*)nullptr + total;  // offset for now
-                total += tri;
+                total += tri_u;
                 for (int r = 0; r < nb; ++r)
                     for (u32 e = r ? up->columnpointer[r] : 0u; e < up->columnpointer[r + 1]; ++e) dd.umask[r / 16] |= 1u << (up->rowindex[e] / 16);
             }
@@ -1706,7 +1778,7 @@ pangulu_sm100_plan* pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_ui
             if (dn.u)
             {
                 dd.u = (T*)nullptr + total;
-                total += tri;
+                total += tri_u;
                 for (int r = 0; r < nb; ++r)
                     for (u32 e = r ? up->columnpointer[r] : 0u; e < up->columnpointer[r + 1]; ++e) dd.umask[r / 16] |= 1u << (up->rowindex[e] / 16);
             }

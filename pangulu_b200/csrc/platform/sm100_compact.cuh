@@ -65,14 +65,26 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity)
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, u32 parity, int site = 0)
 {
     const u32 a = smem_u32(bar);
     u32 ok = 0;
+#ifdef PSM_MBAR_GUARD
+    // debugging aid: name the wait that never completes (site, block, thread, barrier offset in the CTA's shared window)
+    unsigned polls = 0;
+#endif
     do
     {
         asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+#ifdef PSM_MBAR_GUARD
+        if (!ok && ++polls == (1u << 24))
+        {
+            printf("[PanguLU ERROR] mbarrier wait stuck: site %d block %d thread %d barrier@%u parity %u\n", site, (int)blockIdx.x, (int)threadIdx.x, a, parity);
+            __trap();
+        }
+#endif
     } while (!ok);
+    (void)site;
 }
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, u32 bytes, unsigned long long* bar)
 {
@@ -204,7 +216,10 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
     u16* wrow = reinterpret_cast<u16*>(smem_raw + Lay::map_off) + warp * 64;   // [32] full rows of this warp's register tile (0xffff: none)
     u16* wcol = wrow + 32;                                                      // [32] tile columns of it
     const bool diag = D.u.val != nullptr;
-    // the producer (bulk-copy issue, ~300 cycles per item) is lane 0 of the LAST warp
+    // The producer (bulk-copy issue: wait for the slot, ~110 cycles per copy) is lane 0 of the LAST warp, whose piece of the
+    // warp grid is the first to be empty.  All threads keep the ring's phase bits in step, so the issue could rotate over the
+    // warps (-DPSM_CT_DISTRIBUTED_PRODUCERS: lane 0 of warp i % 16 issues item i); measured, the divergence that puts into
+    // every warp costs more than the single producer's delay.
     constexpr int PTID = 480;
     // phase profile: compiled in only with -DPSM_CT_PROFILE (the ten 64-bit counters cost 20 registers per thread)
 #ifdef PSM_CT_PROFILE
@@ -292,7 +307,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         // a block barrier: a warp starts the adds of run i once every warp has ARRIVED after its adds of run i-1 -- which
         // happened a whole run of tensor work ago -- so no warp (in particular not the one that also issues the bulk
         // copies) holds the others up.  Every warp passes here once per run, with or without work.
-        mbar_wait(fbar, flush_bit);
+        mbar_wait(fbar, flush_bit, 1);
         flush_bit ^= 1u;
         if constexpr (kDouble)
         {
@@ -310,10 +325,12 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
 #pragma unroll
                 for (int mt = 0; mt < 4; ++mt)
                 {
+                    if (mt >= mtc) break;   // (warp-uniform: only the tiles the run's grid gave this warp hold anything)
                     const u16 r = wrow[mt * 8 + lr];
 #pragma unroll
                     for (int nt2 = 0; nt2 < 4; ++nt2)
                     {
+                        if (nt2 >= ntc) break;
                         const u32 c2 = *reinterpret_cast<const u32*>(wcol + nt2 * 8 + lc);   // two consecutive columns
 #pragma unroll
                         for (int h = 0; h < 2; ++h)
@@ -495,12 +512,23 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
         // (a lane of a warp that also computes) rarely waits for the slowest warp of the item just consumed
         const int LA = nst > 2 ? nst - 2 : 1;
 
-        // producer step: bulk copies of item i into its slot
+        // producer step: bulk copies of item i into its slot.  Called by EVERY thread for every item, in item order; `mine`
+        // selects the one lane that issues.
         auto produce = [&](int i) {
             const int s = i % nst;
+#ifdef PSM_CT_DISTRIBUTED_PRODUCERS
+            const bool mine = lane == 0 && (i & 15) == warp;   // measured at 100^3: 1.283 s against 1.261 s with one producer
+#else
+            const bool mine = tid == PTID;
+#endif
             lap(7);
-            if (i >= nst) { mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u); empty_bits ^= 1u << s; }  // consumers released the slot
+            if (i >= nst)
+            {
+                if (mine) mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u, 2);   // consumers released the slot
+                empty_bits ^= 1u << s;
+            }
             lap(8);
+            if (!mine) return;
             const u32 it = items[i];
             const CtPairSm& e = pc[it >> 16];
             u32 m = it & 0xffffu;
@@ -531,8 +559,7 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             }
             lap(9);
         };
-        if (tid == PTID)
-            for (int i = 0; i < min(LA, nitems); ++i) produce(i);
+        for (int i = 0; i < min(LA, nitems); ++i) produce(i);
         lap(7);
 
         // ---- pairs of the batch; items of a pair are consecutive in the item list
@@ -556,10 +583,10 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
             const bool warp_active = __any_sync(PSM_FULL, active);
             for (int j = 0; j < cnt; ++j, ++ci)
             {
-                if (tid == PTID && ci + LA < nitems) produce(ci + LA);
+                if (ci + LA < nitems) produce(ci + LA);
                 lap(7);
                 const int s = ci % nst;
-                mbar_wait(bars + s, (full_bits >> s) & 1u);
+                mbar_wait(bars + s, (full_bits >> s) & 1u, 3);
                 full_bits ^= 1u << s;
                 lap(2);
                 const int nch = min(G, nchunk - j * G);   // chunks in this item
@@ -604,19 +631,17 @@ __device__ __noinline__ void ssssm_ctile_cta(unsigned char* smem_raw, int nb, co
                         }
                     }
                   }
-                if (warp_active) __syncwarp();
+                // EVERY lane must have seen the item's phase of the full barrier before the warp releases the slot: a lane still
+                // polling when the slot is refilled would find the barrier one phase further -- same parity as the phase it
+                // waits for -- and spin forever.  (Lanes of a warp drift apart when one of them issues the bulk copies.)
+                __syncwarp();
                 if (lane == 0) mbar_arrive(bars + NSLOT + s);
                 lap(3);
             }
         }
-        // every release must be matched by a wait of the producer, so the barrier bits stay in step
-        if (tid == PTID)
-            for (int j = max(0, nitems - nst); j < nitems; ++j)
-            {
-                const int s = j % nst;
-                mbar_wait(bars + NSLOT + s, (empty_bits >> s) & 1u);
-                empty_bits ^= 1u << s;
-            }
+        // the releases of the last nst items are never waited for: their phases are complete once every warp has passed the
+        // block barrier that precedes the next use of the ring (top of the next batch / the task's epilogue); account for them
+        for (int j = max(0, nitems - nst); j < nitems; ++j) empty_bits ^= 1u << (j % nst);
     }
     if (have_run) flush();
     st.full_bits = full_bits;
@@ -735,7 +760,8 @@ __device__ __forceinline__ void dense_store_b(const DenseOp<T>& B, int k, int cp
 template <class T>
 struct DiagDense
 {
-    T* u;            // U   (upper half incl. diagonal) in the B-operand layout [chunk][nb][20], or null
+    T* u;            // U   (upper half incl. diagonal) in the B-operand layout [chunk][nb][20], followed by the nb RECIPROCALS of the
+                     // (clamped) pivots, or null
     T* lt;           // L^T (strict lower half, transposed), same layout, or null
     u32 umask[16];   // umask[K] bit J: sub-block (rows 16K.., columns 16J..) of U has entries
     u32 ltmask[16];
@@ -749,7 +775,7 @@ struct CpLayout
 {
     static constexpr size_t x_bytes = (size_t)256 * PSM_CP_LDX * sizeof(T);
     static constexpr size_t sub_bytes = (size_t)16 * PSM_CT_BLD * sizeof(T);     // one 16 x 16 sub-block of Tm
-    static constexpr size_t tbuf_bytes = 16 * sub_bytes;                            // one column block (all K)
+    static constexpr size_t tbuf_bytes = 16 * sub_bytes + 16 * sizeof(T);           // one column block (all K) + the 16 pivot reciprocals of the chunk
     static constexpr size_t total = x_bytes + 2 * tbuf_bytes + 4 * (260 + 64) + 2 * 256 + 64;  // + pointer / prefix / inverse-map staging
 };
 
@@ -762,9 +788,18 @@ __device__ __forceinline__ void diag_densify(int nb, const GetrfTask<T>& G, cons
     const int warp = threadIdx.x / PSM_WARP, lane = threadIdx.x % PSM_WARP, nw = blockDim.x / PSM_WARP;
     (void)nb;
     if (DD.u)
+    {
+        // The compact panel solves multiply by the reciprocal of the pivot (one division per pivot HERE instead of a chain of
+        // 16 dependent divisions per row and k-chunk there; a result differs from the reference's x / pivot by one rounding).
+        T* rcp = DD.u + (size_t)(nb / 16) * nb * PSM_CT_BLD;
         for (int r = G.c0 + warp; r < G.c1; r += nw)   // row r of U (CSR, diagonal first); only the task's group
-            for (u32 e = col_begin(G.upper.ptr, r) + lane; e < G.upper.ptr[r + 1]; e += PSM_WARP)
+        {
+            const u32 e0 = col_begin(G.upper.ptr, r), e1 = G.upper.ptr[r + 1];
+            for (u32 e = e0 + lane; e < e1; e += PSM_WARP)
                 DD.u[((size_t)(r / 16) * nb + G.upper.idx[e]) * PSM_CT_BLD + (r % 16)] = G.upper.val[e];
+            if (lane == 0 && e1 > e0) rcp[r] = vrcp(clamp_pivot(G.upper.val[e0]));
+        }
+    }
     if (DD.lt)
         for (int k = G.c0 + warp; k < G.c1; k += nw)   // column k of L (CSC): L(c,k) = L^T(k,c)
             for (u32 e = col_begin(G.lower.ptr, k) + lane; e < G.lower.ptr[k + 1]; e += PSM_WARP)
@@ -822,14 +857,17 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
         u32 need = 0;
         for (int K = 0; K <= J; ++K)
             if (((kmask >> K) & 1u) && (K == J || ((tmask[K] >> J) & 1u))) need |= 1u << K;
-        mbar_expect_tx(cbars + par, (u32)(__popc(need) * Lay::sub_bytes));
+        mbar_expect_tx(cbars + par, (u32)(__popc(need) * Lay::sub_bytes + (gessm ? 0 : 16 * sizeof(T))));
         for (int K = 0; K <= J; ++K)
             if ((need >> K) & 1u)
                 bulk_g2s(tb + (size_t)K * Lay::sub_bytes, Tm + ((size_t)K * nb + 16 * J) * BLD, (u32)Lay::sub_bytes, cbars + par);
+        if (!gessm) bulk_g2s(tb + 16 * Lay::sub_bytes, Tm + (size_t)(nb / 16) * nb * BLD + 16 * J, (u32)(16 * sizeof(T)), cbars + par);   // pivot reciprocals
     };
+    // the copies are issued by a lane of a warp that has no part in the substitution (the issue costs ~110 cycles per copy)
+    constexpr int ISSUER = 256;
     int Jcur = kmask ? (__ffs(kmask) - 1) : -1;
     int par = 0;
-    if (tid == 0 && Jcur >= 0) issue(Jcur, 0);
+    if (tid == ISSUER && Jcur >= 0) issue(Jcur, 0);
     // Gather (and, at the end, scatter) run as FLAT loops over the slice's entries with the block's pointer array and
     // inverse row map staged in shared memory: many independent loads in flight instead of a chain of dependent ones
     // per column.
@@ -951,8 +989,10 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
     {
         const u32 rest = kmask & ~((2u << Jcur) - 1u);
         const int Jnext = rest ? (__ffs(rest) - 1) : -1;
-        if (tid == 0 && Jnext >= 0) issue(Jnext, par ^ 1);   // prefetch the next column block
-        mbar_wait(cbars + par, (bits >> par) & 1u);
+#ifdef PSM_CP_ISSUE_EARLY
+        if (tid == ISSUER && Jnext >= 0) issue(Jnext, par ^ 1);
+#endif
+        mbar_wait(cbars + par, (bits >> par) & 1u, 4);
         bits ^= 1u << par;
         clap(2);
         const T* Tb = reinterpret_cast<const T*>(tb0 + (size_t)par * Lay::tbuf_bytes);
@@ -1006,10 +1046,16 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
             __syncthreads();
         }
         clap(3);
+        // prefetch the next column block into the other buffer (its readers finished before the barrier that ended the previous
+        // chunk) while the substitution runs
+#ifndef PSM_CP_ISSUE_EARLY
+        if (tid == ISSUER && Jnext >= 0) issue(Jnext, par ^ 1);
+#endif
         // ---- 16-column substitution against the diagonal sub-block, one thread per row
         if (tid < R)
         {
             const T* Tjj = Tb + (size_t)Jcur * 16 * BLD;   // Tm(16J + k, 16J + c) at [c*20 + k]
+            const T* rcp = reinterpret_cast<const T*>(tb0 + (size_t)par * Lay::tbuf_bytes + 16 * Lay::sub_bytes);
             T x[16];
 #pragma unroll
             for (int c = 0; c < 16; ++c) x[c] = X[(Jcur * 16 + c) * LDX + tid];
@@ -1018,7 +1064,11 @@ __device__ __noinline__ void panel_compact_cta(unsigned char* smem_raw, int nb, 
 #pragma unroll
             for (int k = 0; k < 16; ++k)
             {
+#ifdef PSM_CP_DIVIDE
                 if (!gessm) x[k] = vdiv(x[k], clamp_pivot(Tjj[k * BLD + k]));
+#else
+                if (!gessm) x[k] = vmul(x[k], rcp[k]);
+#endif
 #pragma unroll
                 for (int c = 0; c < 16; ++c)
                     if (c > k) fnma(x[c], x[k], Tjj[c * BLD + k]);

@@ -22,10 +22,21 @@ namespace psm {
 __device__ __forceinline__ u32 col_begin(const u32* ptr, int j) { return j == 0 ? 0u : ptr[j]; }
 
 // x -= v with a global-memory reduction (several CTAs updating one destination)
-__device__ __forceinline__ void red_sub(double* a, double v) { atomicAdd(a, -v); }
-__device__ __forceinline__ void red_sub(float* a, float v) { atomicAdd(a, -v); }
-__device__ __forceinline__ void red_sub(pangulu_sm100_c64* a, pangulu_sm100_c64 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
-__device__ __forceinline__ void red_sub(pangulu_sm100_c32* a, pangulu_sm100_c32 v) { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
+// Fire-and-forget global reductions (SASS REDG).  atomicAdd on a pointer whose state space the compiler cannot prove (the
+// value arrays are reached through descriptors in memory) compiles to a GENERIC returning atomic plus a shared-memory CAS
+// fallback, and the thread waits an L2 round trip for the predicate of every single add.
+__device__ __forceinline__ void red_add_global(double* a, double v)
+{
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_global(float* a, float v)
+{
+    asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(a)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void red_sub(double* a, double v) { red_add_global(a, -v); }
+__device__ __forceinline__ void red_sub(float* a, float v) { red_add_global(a, -v); }
+__device__ __forceinline__ void red_sub(pangulu_sm100_c64* a, pangulu_sm100_c64 v) { red_add_global(&a->re, -v.re); red_add_global(&a->im, -v.im); }
+__device__ __forceinline__ void red_sub(pangulu_sm100_c32* a, pangulu_sm100_c32 v) { red_add_global(&a->re, -v.re); red_add_global(&a->im, -v.im); }
 
 __device__ inline void vadd(double& x, double a) { x += a; }
 __device__ inline void vadd(float& x, float a) { x += a; }
@@ -647,12 +658,7 @@ template <> __device__ inline void atomic_sub<pangulu_sm100_c64>(pangulu_sm100_c
 template <> __device__ inline void atomic_sub<pangulu_sm100_c32>(pangulu_sm100_c32* a, pangulu_sm100_c32 v)
 { atomicAdd(&a->re, -v.re); atomicAdd(&a->im, -v.im); }
 
-__device__ inline double vmul(double a, double b) { return a * b; }
-__device__ inline float vmul(float a, float b) { return a * b; }
-__device__ inline pangulu_sm100_c64 vmul(pangulu_sm100_c64 a, pangulu_sm100_c64 b)
-{ pangulu_sm100_c64 r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
-__device__ inline pangulu_sm100_c32 vmul(pangulu_sm100_c32 a, pangulu_sm100_c32 b)
-{ pangulu_sm100_c32 r; r.re = a.re * b.re - a.im * b.im; r.im = a.re * b.im + a.im * b.re; return r; }
+// (vmul: sm100_types.cuh)
 
 // y -= A x, A in CSC: one warp per column
 template <class T>
@@ -1263,6 +1269,7 @@ struct MegaParams
     const MegaPush<T>* pushes;
     int multi;              // 1: flags may be written by peers -> system-scope acquire
     unsigned long long* trace;  // optional: per task {fetch, start, end} in ns (globaltimer), else null
+    int4* progress;             // optional (host-mapped): per CTA {task, kind, first argument, 0 waiting / 1 running / 2 done}
 };
 __device__ __forceinline__ unsigned long long global_ns()
 {
@@ -1421,6 +1428,11 @@ mega_kernel(const MegaParams<T> P)
         if (t >= P.ntask) break;
         const MegaTask mt = P.tasks[t];
         if (P.trace && tid == 0) P.trace[3 * (size_t)t] = global_ns();
+        if (P.progress && tid == 0)
+        {
+            volatile int* pg = reinterpret_cast<volatile int*>(P.progress + blockIdx.x);
+            pg[0] = t; pg[1] = mt.kind; pg[2] = mt.a; pg[3] = 0;
+        }
         switch (mt.kind)
         {
         case MEGA_TILE:
@@ -1442,6 +1454,7 @@ mega_kernel(const MegaParams<T> P)
             }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 1;
             if (mt.kind == MEGA_CTILE)
                 ssssm_ctile_cta<T, ct_traits<T>::TN, ct_traits<T>::STAGES>(smem_raw, nb, D, P.cpairs, P.ops, mt.b & 0xffff, mt.b >> 16, ct_state);
             else if (mt.kind == MEGA_TILE)
@@ -1472,6 +1485,7 @@ mega_kernel(const MegaParams<T> P)
             if (tid == 0) spin_until_zero(P.remaining + id.x);
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 1;
             if (mt.kind == MEGA_GETRF_SMEM)
                 getrf_smem_cta<T, 512>(smem_raw, nb, G);
             else if (mt.kind == MEGA_GETRF_DENSE)
@@ -1514,6 +1528,7 @@ mega_kernel(const MegaParams<T> P)
             }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 1;
             diag_densify<T>(nb, G, P.dds[P.getrf_dd[mt.a]]);
             asm volatile("fence.proxy.async;" ::: "memory");
             __threadfence();
@@ -1537,6 +1552,7 @@ mega_kernel(const MegaParams<T> P)
             }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 1;
             panel_compact_cta<T>(smem_raw, nb, Q, P.ops[Q.dense], P.dds[cpt.dd], cpt.r0, cp_state);
             asm volatile("fence.proxy.async;" ::: "memory");   // the compact copy just written is read with bulk copies
             __threadfence();
@@ -1565,6 +1581,7 @@ mega_kernel(const MegaParams<T> P)
             }
             __syncthreads();
             if (P.trace && tid == 0) P.trace[3 * (size_t)t + 1] = global_ns();
+            if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 1;
             // one task = 64 consecutive rows/columns of the block (four per warp); the diagonal half they are solved
             // against is staged in shared memory when it fits.  The last sub-task of a block to finish publishes it.
             T* x = reinterpret_cast<T*>(smem_raw) + (size_t)warp * nb;
@@ -1609,6 +1626,7 @@ mega_kernel(const MegaParams<T> P)
         }
         __syncthreads();
         if (P.trace && tid == 0) P.trace[3 * (size_t)t + 2] = global_ns();
+        if (P.progress && tid == 0) ((volatile int*)(P.progress + blockIdx.x))[3] = 2;
     }
 }
 

@@ -80,6 +80,27 @@ __device__ inline pangulu_sm100_c32 vdiv(pangulu_sm100_c32 a, pangulu_sm100_c32 
     return r;
 }
 
+__device__ inline double vmul(double a, double b) { return a * b; }
+__device__ inline float vmul(float a, float b) { return a * b; }
+__device__ inline pangulu_sm100_c64 vmul(pangulu_sm100_c64 a, pangulu_sm100_c64 b)
+{
+    pangulu_sm100_c64 r;
+    r.re = a.re * b.re - a.im * b.im;
+    r.im = a.re * b.im + a.im * b.re;
+    return r;
+}
+__device__ inline pangulu_sm100_c32 vmul(pangulu_sm100_c32 a, pangulu_sm100_c32 b)
+{
+    pangulu_sm100_c32 r;
+    r.re = a.re * b.re - a.im * b.im;
+    r.im = a.re * b.im + a.im * b.re;
+    return r;
+}
+__device__ inline double vrcp(double p) { return 1.0 / p; }
+__device__ inline float vrcp(float p) { return 1.0f / p; }
+__device__ inline pangulu_sm100_c64 vrcp(pangulu_sm100_c64 p) { pangulu_sm100_c64 o; o.re = 1.0; o.im = 0.0; return vdiv(o, p); }
+__device__ inline pangulu_sm100_c32 vrcp(pangulu_sm100_c32 p) { pangulu_sm100_c32 o; o.re = 1.0f; o.im = 0.0f; return vdiv(o, p); }
+
 // Pivot clamp of the CPU platform (pangulu_platform_0100000.c:80-84,153-157):
 //   if (fabs(pivot) < PANGULU_TOL) pivot = PANGULU_TOL;
 // fabs() on a C99 complex converts to double first, i.e. looks at the REAL part only, and the

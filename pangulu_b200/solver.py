@@ -107,6 +107,20 @@ class PanguLU:
     def reset_values(self, also_device: bool = True) -> None:
         self.L.pangulu_sm100_driver_reset_values(self._h, int(also_device))
 
+    def update_values(self, values: np.ndarray) -> float:
+        """New numerical values on the pattern the solver was built for (the data array of the sorted CSC matrix given to
+        the constructor): nnz(A) values travel to the GPU and are scattered into the block value region by a kernel
+        (preprocessing on the device, include/pangulu_sm100_driver.h).  Resident mode.  Returns seconds."""
+        v = np.ascontiguousarray(values, dtype=self.dtype)
+        assert v.shape == self._value.shape
+        self._value = v
+        return float(self.L.pangulu_sm100_driver_update_values(self._h, self._colptr.ctypes.data, self._rowidx.ctypes.data, v.ctypes.data))
+
+    def device_mirrors(self, clear_first: bool = True) -> int:
+        """Rebuild the CSR mirrors of the strictly-lower blocks on the GPU; returns the number of bytes in which the device's
+        index region differs from the host-built one (0 = bit-identical)."""
+        return int(self.L.pangulu_sm100_driver_device_mirrors(self._h, int(clear_first)))
+
     def gstrf_enqueue(self) -> None:
         """Resident mode: enqueue the factorisation on the module's stream without synchronising."""
         self.L.pangulu_sm100_driver_gstrf_enqueue(self._h)
