@@ -1452,9 +1452,10 @@ void PSM(sptrsv)(pangulu_inblock_idx nb, pangulu_storage_slot_t* s, calculate_ty
     // uplo 0: s is a lower half / strictly-lower pattern in CSC; uplo 1: s is the UPPER half of a diagonal block
     Blk<T> S = uplo == 0 ? blk_csc(s) : blk_upper_diag(s);
     constexpr int THREADS = 256;
-    const size_t smem = (size_t)nb * sizeof(T);
+    // the half's arrays are staged next to x in shared memory when they fit (the kernel decides)
+    const size_t smem = std::max((size_t)nb * sizeof(T), (size_t)g.max_smem_optin - 1024);
     set_smem(sptrsv_kernel<T, THREADS>, smem);
-    sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, S, (T*)xval, (int)uplo);
+    sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, S, (T*)xval, (int)uplo, (unsigned)smem);
     CK_LAST();
     g.launches[K_AUX]++;
 }
@@ -1527,19 +1528,19 @@ void pangulu_sm100_solve_plan_execute(pangulu_sm100_solve_plan* sp, calculate_ty
     const size_t bytes = (size_t)sp->block_length * nb * sizeof(T);
     CK(cudaMemcpyAsync(sp->d_x, x_host, bytes, cudaMemcpyHostToDevice, g.stream));
     constexpr int THREADS = 256;
-    const size_t smem = (size_t)nb * sizeof(T);
+    const size_t smem = std::max((size_t)nb * sizeof(T), (size_t)g.max_smem_optin - 1024);
     set_smem(sptrsv_kernel<T, THREADS>, smem);
     for (long long k = 0; k < sp->block_length; ++k)          // forward: x_k <- L_kk^-1 (x_k - sum_{j<k} L_kj x_j)
     {
         const long long nblk = sp->lptr[k + 1] - sp->lptr[k];
         if (nblk) solve_spmv_row_kernel<T><<<(unsigned)nblk, 256, 0, g.stream>>>(nb, sp->d_l + sp->lptr[k], sp->d_x, k * nb);
-        if (sp->dlo[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dlo[k], sp->d_x + k * nb, 0);
+        if (sp->dlo[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dlo[k], sp->d_x + k * nb, 0, (unsigned)smem);
     }
     for (long long k = sp->block_length - 1; k >= 0; --k)      // backward: x_k <- U_kk^-1 (x_k - sum_{j>k} U_kj x_j)
     {
         const long long nblk = sp->uptr[k + 1] - sp->uptr[k];
         if (nblk) solve_spmv_row_kernel<T><<<(unsigned)nblk, 256, 0, g.stream>>>(nb, sp->d_u + sp->uptr[k], sp->d_x, k * nb);
-        if (sp->dup[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dup[k], sp->d_x + k * nb, 1);
+        if (sp->dup[k].val) sptrsv_kernel<T, THREADS><<<1, THREADS, smem, g.stream>>>(nb, sp->dup[k], sp->d_x + k * nb, 1, (unsigned)smem);
     }
     CK_LAST();
     g.launches[K_AUX] += 4 * sp->block_length;

@@ -697,20 +697,38 @@ __global__ void vecadd_kernel(long long n, T* __restrict__ b, const T* __restric
 // 1 = upper CSR backward (row dot products, diagonal first in each row, pivot clamp of
 // pangulu_platform_0100000.c:500-503)
 template <class T, int THREADS>
-__global__ void __launch_bounds__(THREADS) sptrsv_kernel(int nb, Blk<T> S, T* __restrict__ xg, int uplo)
+__global__ void __launch_bounds__(THREADS) sptrsv_kernel(int nb, Blk<T> S, T* __restrict__ xg, int uplo, unsigned smem_bytes)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* x = reinterpret_cast<T*>(smem_raw);
     __shared__ T part[THREADS / PSM_WARP];
     for (int i = threadIdx.x; i < nb; i += THREADS) x[i] = xg[i];
+    // The substitution is a chain of nb dependent steps; with the half's arrays in global memory every step pays an L2 round
+    // trip (~130 us per 256 x 256 half).  Stage pointers, indices and values in shared memory when they fit.
+    {
+        const u32 nnz = S.ptr[nb];
+        const size_t off_ptr = ((size_t)nb * sizeof(T) + 15) & ~(size_t)15;
+        const size_t off_val = (off_ptr + 4 * (size_t)(nb + 1) + 15) & ~(size_t)15;
+        const size_t off_idx = off_val + (size_t)nnz * sizeof(T);
+        if (off_idx + 2 * (size_t)nnz <= smem_bytes)
+        {
+            u32* sptr = reinterpret_cast<u32*>(smem_raw + off_ptr);
+            T* sval = reinterpret_cast<T*>(smem_raw + off_val);
+            u16* sidx = reinterpret_cast<u16*>(smem_raw + off_idx);
+            for (int i = threadIdx.x; i <= nb; i += THREADS) sptr[i] = i == 0 ? 0u : S.ptr[i];
+            for (u32 e = threadIdx.x; e < nnz; e += THREADS) { sval[e] = S.val[e]; sidx[e] = S.idx[e]; }
+            S.ptr = sptr; S.val = sval; S.idx = sidx;
+        }
+    }
     __syncthreads();
     if (uplo == 0)
     {
         for (int i = 0; i < nb; ++i)
         {
-            const T xi = x[i];
-            __syncthreads();
-            for (u32 e = col_begin(S.ptr, i) + threadIdx.x; e < S.ptr[i + 1]; e += THREADS) fnma(x[S.idx[e]], S.val[e], xi);
+            const u32 e0 = col_begin(S.ptr, i), e1 = S.ptr[i + 1];
+            if (e0 == e1) continue;   // (uniform: nothing to apply, nothing to wait for)
+            const T xi = x[i];         // final: every earlier column was applied before the barrier that ended its step
+            for (u32 e = e0 + threadIdx.x; e < e1; e += THREADS) fnma(x[S.idx[e]], S.val[e], xi);
             __syncthreads();
         }
     }
@@ -720,6 +738,25 @@ __global__ void __launch_bounds__(THREADS) sptrsv_kernel(int nb, Blk<T> S, T* __
         {
             const u32 r0 = col_begin(S.ptr, i), r1 = S.ptr[i + 1];
             if (r0 == r1) continue;
+            if (r1 - r0 <= 1 + PSM_WARP)
+            {
+                // short row: one warp, no block barrier for the partial sums
+                if (threadIdx.x < PSM_WARP)
+                {
+                    T s = zero<T>();
+                    const u32 e = r0 + 1 + threadIdx.x;
+                    if (e < r1) fma_acc(s, S.val[e], x[S.idx[e]]);
+                    s = warp_sum(s);
+                    if (threadIdx.x == 0)
+                    {
+                        T xi = x[i];
+                        vsub(xi, s);
+                        x[i] = vdiv(xi, clamp_pivot(S.val[r0]));
+                    }
+                }
+                __syncthreads();
+                continue;
+            }
             T s = zero<T>();
             for (u32 e = r0 + 1 + threadIdx.x; e < r1; e += THREADS) fma_acc(s, S.val[e], x[S.idx[e]]);
             s = warp_sum(s);
