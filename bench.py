@@ -58,6 +58,7 @@ WORKLOADS = {
     # (n = 50 000 already holds 6.3e8 stored entries = 10 GB of CR64 values): the size is a parameter, default 40 000
     "circuit_cr64": ("circuit_like", "cr64", 40000, [8000, 6000, 4000]),
 }
+MULTI_LOOKAHEAD = 2   # look-ahead window (waves) with several ranks; measured sweep in profiles/r02_multi_lookahead_sweep.txt
 DTYPES = {"r64": "float64", "r32": "float32", "cr64": "complex128", "cr32": "complex64"}
 # measured seconds of ONE reference gstrf (8 ranks over the shared-memory MPI shim) by sample size, used to pick the largest
 # sample whose warmup + steps fit the reference arm's budget; anything not listed is estimated by flop count
@@ -79,6 +80,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-sample", action="store_true", help="skip the same_config_sample block")
+    ap.add_argument("--schedule", type=int, default=-1, help="placement of the updates: 0 lazy, 1 eager, 2 windowed (default: the driver's, 2)")
+    ap.add_argument("--lookahead", type=int, default=-1, help="window of the windowed schedule in waves (default: 2 on one GPU, MULTI_LOOKAHEAD on several)")
     ap.add_argument("--no-classes", action="store_true", help="skip the traced run that attributes device time to kernel classes")
     return ap.parse_args()
 
@@ -406,7 +409,9 @@ def run_ours(a):
     label = workload_name(gen, size, vtype, a.nb)
     L = _lib.load(vtype)
     t0 = time.time()
-    s = PanguLU(A, nb=a.nb, mode=1, rank=rank, nproc=world)
+    sched_kw = {"schedule": a.schedule if a.schedule >= 0 else 2,
+                "lookahead": a.lookahead if a.lookahead >= 0 else (2 if world == 1 else MULTI_LOOKAHEAD)}
+    s = PanguLU(A, nb=a.nb, mode=1, rank=rank, nproc=world, **sched_kw)
     init_host = time.time() - t0
     t0 = time.time()
     if world > 1:

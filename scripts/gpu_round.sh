@@ -14,6 +14,9 @@ echo "bench rc=$?" >> $O/bench_default.err
 # launch list of the bench command (shares of the step, not absolute times)
 ( time timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_bench.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-sample --no-classes --no-e2e ) > $O/launches.log 2>&1
+# one full-section capture of the dominant routine as a stand-alone kernel (per-wave executor), 64^3: a launch late in the factorisation
+( time timeout 600 ncu --set full --clock-control none --import-source on -k regex:ssssm_ctile_kernel --launch-skip 150 --launch-count 1 -f -o $O/ncu_ctile_full \
+    python scripts/quick_bench.py --case p3 --size 64 --nb 256 --steps 1 --profile 0 --mode 1 --opt executor=0 ) > $O/ncu_ctile_full.log 2>&1
 for w in laplace2d_1000 stencil27_64 stencil27_64_r32 circuit_cr64; do
   ( time timeout 900 python bench.py --workload $w ) > $O/bench_$w.json 2> $O/bench_$w.err
   echo "bench rc=$?" >> $O/bench_$w.err
