@@ -150,6 +150,10 @@ typedef struct pangulu_sm100_plan pangulu_sm100_plan;
 pangulu_sm100_plan *pangulu_sm100_plan_create(pangulu_inblock_idx nb, pangulu_uint64_t nwave,
                                               const pangulu_uint64_t *waves, const pangulu_task_t *tasks);
 void pangulu_sm100_plan_execute(pangulu_sm100_plan *plan);
+/* Execute the plan and copy the values of the n given blocks to their host arrays (slot->d_value -> slot->value, pinned) as
+ * the blocks become final, overlapped with the rest of the factorisation; returns when kernel and copies are complete.
+ * (The reference downloads every block after the call that finishes it, pangulu_platform_0201000.cu:196-201.) */
+void pangulu_sm100_plan_execute_download(pangulu_sm100_plan *plan, pangulu_uint64_t n, pangulu_storage_slot_t **slots);
 /* execute waves [w0, w1) only (multi-GPU driver interleaves block exchange between waves) */
 void pangulu_sm100_plan_execute_range(pangulu_sm100_plan *plan, pangulu_uint64_t w0, pangulu_uint64_t w1);
 void pangulu_sm100_plan_destroy(pangulu_sm100_plan *plan);

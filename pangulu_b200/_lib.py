@@ -38,7 +38,7 @@ EXTENSION_FUNCTIONS = [
     "pangulu_sm100_plan_flag_offset2", "pangulu_sm100_plan_expect_remote2", "pangulu_sm100_plan_add_push3",
     "pangulu_sm100_ipc_close", "pangulu_sm100_plan_task_work",
     "pangulu_sm100_solve_plan_create", "pangulu_sm100_solve_plan_execute", "pangulu_sm100_solve_plan_destroy",
-    "pangulu_sm100_scatter_values", "pangulu_sm100_mirror_patterns",
+    "pangulu_sm100_scatter_values", "pangulu_sm100_mirror_patterns", "pangulu_sm100_plan_execute_download",
 ]
 #: host driver, include/pangulu_sm100_driver.h
 DRIVER_FUNCTIONS = [
@@ -189,6 +189,7 @@ def load(vtype: str = "r64") -> C.CDLL:
     L.pangulu_sm100_driver_factor_check.argtypes = [vp]
     L.pangulu_sm100_scatter_values.argtypes = [vp, C.c_size_t, vp, vp, vp, u64]
     L.pangulu_sm100_mirror_patterns.argtypes = [C.c_uint16, u64, vp]
+    L.pangulu_sm100_plan_execute_download.argtypes = [vp, u64, vp]
     L.pangulu_sm100_driver_update_values.argtypes = [vp, vp, vp, vp]
     L.pangulu_sm100_driver_update_values.restype = C.c_double
     L.pangulu_sm100_driver_device_mirrors.argtypes = [vp, C.c_int]

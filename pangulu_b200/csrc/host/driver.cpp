@@ -253,9 +253,13 @@ void pangulu_gstrf(pangulu_gstrf_options* gstrf_options, void** pangulu_handle)
             h->plan = pangulu_sm100_plan_create((pangulu_inblock_idx)h->nb, h->sched.wave_ptr.size() - 1, (const pangulu_uint64_t*)h->sched.wave_ptr.data(),
                                                 h->sched.tasks.data());
         PSM(memcpy)(B.d_buf, B.h_buf, B.value_bytes, 0);
-        pangulu_sm100_plan_execute(h->plan);
+        // the finished factors travel back while the factorisation is still running (pieces of consecutive owned blocks, as
+        // their done flags come up)
+        std::vector<pangulu_storage_slot_t*> own;
+        own.reserve(B.n_own_offdiag + 2 * B.n_own_diag);
+        for (size_t i = 0; i < B.n_own_offdiag + 2 * B.n_own_diag; ++i) own.push_back(&B.slots[i]);
+        pangulu_sm100_plan_execute_download(h->plan, own.size(), own.data());
         PSM(synchronize)();
-        PSM(memcpy)(B.h_buf, B.d_buf, B.own_value_bytes, 1);
     }
     else
     {

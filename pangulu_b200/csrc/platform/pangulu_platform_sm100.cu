@@ -6,6 +6,7 @@
 // every failure prints "[PanguLU ERROR] ..." and exits, as the reference platform does
 // (src/platforms/02_NONSHAREDMEM/01_GPU/000_CUDA/pangulu_platform_0201000.cu:31-50).
 #include <cuda_runtime.h>
+#include <time.h>
 #include <algorithm>
 #include <array>
 #include <cstdio>
@@ -1942,6 +1943,102 @@ void pangulu_sm100_plan_execute(pangulu_sm100_plan* pl)
     if (!pl) fatal(__FILE__, __LINE__, "null plan", nullptr);
     if (pl->mega && g.opt.executor == 1) { run_mega(pl); return; }
     pangulu_sm100_plan_execute_range(pl, 0, pl->wave_step.size() - 1);
+}
+
+// Execute the plan and bring the values of the given blocks to their host arrays WHILE the factorisation runs: a block's
+// values are final once its done flag(s) are up, long before the kernel ends (the leaves of the elimination tree finish
+// first).  The host polls the flag array through a non-blocking copy stream and enqueues device -> host copies of
+// address-contiguous pieces of blocks (the driver's layout: one piece = up to 128 MB of consecutive blocks) as soon as
+// every block of a piece is final; what is left goes after the kernel.  The reference downloads every block right after
+// the kernel call that finishes it (pangulu_platform_0201000.cu:196-201, 639-640, 680, 714); this is the same overlap without
+// a launch per block.  Host arrays must be pinned for the copies to overlap.
+void pangulu_sm100_plan_execute_download(pangulu_sm100_plan* pl, pangulu_uint64_t n, pangulu_storage_slot_t** slots)
+{
+    if (!pl) fatal(__FILE__, __LINE__, "null plan", nullptr);
+    const int nb = pl->nb;
+    if (!(pl->mega && g.opt.executor == 1) || pl->nids == 0)
+    {
+        pangulu_sm100_plan_execute(pl);
+        pangulu_sm100_download_blocks((pangulu_inblock_idx)nb, n, slots);
+        CK(cudaStreamSynchronize(g.stream));
+        return;
+    }
+    struct Piece { char* d; char* h; size_t bytes; std::vector<int> flags; bool issued; };
+    std::vector<Piece> pieces;
+    const size_t piece_max = (size_t)128 << 20;
+    for (pangulu_uint64_t i = 0; i < n; ++i)
+    {
+        const pangulu_storage_slot_t* sl = slots[i];
+        const size_t bytes = sizeof(T) * (size_t)slot_nnz(nb, sl);
+        if (!bytes) continue;
+        char* d = (char*)sl->d_value;
+        char* h = (char*)sl->value;
+        // consecutive blocks with the same (small, alignment) gap on both sides extend the piece; the gap bytes travel too
+        long long gap = -1;
+        if (!pieces.empty())
+        {
+            const long long gd = d - (pieces.back().d + pieces.back().bytes), gh = h - (pieces.back().h + pieces.back().bytes);
+            if (gd == gh && gd >= 0 && gd < 256 && pieces.back().bytes + (size_t)gd + bytes <= piece_max) gap = gd;
+        }
+        if (gap < 0) { pieces.push_back({d, h, 0, {}, false}); gap = 0; }
+        Piece& pc = pieces.back();
+        pc.bytes += (size_t)gap + bytes;
+        bool any = false;
+        for (int gr = 0; gr < 4; ++gr)   // (groups of a diagonal half are keyed value pointer + group)
+        {
+            auto it = pl->ids.find((const char*)sl->d_value + gr);
+            if (it == pl->ids.end()) break;
+            pc.flags.push_back(it->second);
+            any = true;
+        }
+        if (!any) pc.flags.push_back(-1);   // no task finalises it: only after the kernel
+    }
+    static cudaStream_t copy_stream = nullptr;
+    static int* h_flags = nullptr;
+    static size_t h_flags_cap = 0;
+    if (!copy_stream) CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    if (h_flags_cap < pl->nids)
+    {
+        if (h_flags) CK(cudaFreeHost(h_flags));
+        CK(cudaHostAlloc((void**)&h_flags, pl->nids * sizeof(int), cudaHostAllocDefault));
+        h_flags_cap = pl->nids;
+    }
+    run_mega(pl);
+    size_t left = pieces.size();
+    while (left)
+    {
+        const bool finished = cudaStreamQuery(g.stream) == cudaSuccess;
+        if (!finished)
+        {
+            CK(cudaMemcpyAsync(h_flags, pl->mp.done, pl->nids * sizeof(int), cudaMemcpyDeviceToHost, copy_stream));
+            CK(cudaStreamSynchronize(copy_stream));
+        }
+        size_t issued_now = 0;
+        for (Piece& pc : pieces)
+        {
+            if (pc.issued) continue;
+            bool ready = finished;
+            if (!ready)
+            {
+                ready = true;
+                for (int f : pc.flags)
+                    if (f < 0 || h_flags[f] == 0) { ready = false; break; }
+            }
+            if (!ready) continue;
+            CK(cudaMemcpyAsync(pc.h, pc.d, pc.bytes, cudaMemcpyDeviceToHost, copy_stream));
+            pc.issued = true;
+            ++issued_now;
+            --left;
+        }
+        if (!issued_now && !finished)
+        {
+            struct timespec ts = {0, 300000};
+            nanosleep(&ts, nullptr);
+        }
+    }
+    CK(cudaStreamSynchronize(copy_stream));
+    CK(cudaStreamSynchronize(g.stream));
+    g.launches[K_AUX] += (long long)pieces.size();
 }
 
 // persistent executor trace: for task i, out[4i..4i+3] = {kind, fetch_ns, start_ns, end_ns}; returns the task count
