@@ -84,6 +84,7 @@ def parse_args():
     ap.add_argument("--no-sample", action="store_true", help="skip the same_config_sample block")
     ap.add_argument("--schedule", type=int, default=-1, help="placement of the updates: 0 lazy, 1 eager, 2 windowed (default: the driver's, 2)")
     ap.add_argument("--lookahead", type=int, default=-1, help="window of the windowed schedule in waves (default: 2 on one GPU, MULTI_LOOKAHEAD on several)")
+    ap.add_argument("--defer", type=int, default=-1, help="persistent executor: tasks a CTA may set aside while their dependencies are outstanding (default: the library's)")
     ap.add_argument("--no-classes", action="store_true", help="skip the traced run that attributes device time to kernel classes")
     return ap.parse_args()
 
@@ -411,6 +412,8 @@ def run_ours(a):
     label = workload_name(gen, size, vtype, a.nb)
     L = _lib.load(vtype)
     t0 = time.time()
+    if a.defer >= 0:
+        assert L.pangulu_sm100_set_option(b"defer", a.defer) == 0
     sched_kw = {"schedule": a.schedule if a.schedule >= 0 else 2,
                 "lookahead": a.lookahead if a.lookahead >= 0 else (2 if world == 1 else MULTI_LOOKAHEAD)}
     s = PanguLU(A, nb=a.nb, mode=1, rank=rank, nproc=world, **sched_kw)

@@ -92,6 +92,7 @@ struct Options
     long long cpanel = 1;       // plans: TSTRF/GESSM of blocks with a compact copy as dense triangular solves on the DMMA pipe
     long long dense_all_panels = 0;  // plans: every eligible panel block gets a compact copy (multi-GPU: a peer may need it)
     long long ct_gmax = 4, ct_minst = 2;  // compact tile ring policy: chunks per item (at most), items the ring must hold (at least)
+    long long defer = 0;        // persistent executor: tasks a CTA may set aside while their dependencies are outstanding (0 = wait in place)
     long long progress = 0;     // persistent executor: per-CTA progress board in host-mapped memory, dumped when a launch fails (debugging aid)
     long long spin_timeout_ms = 30000;  // persistent executor: a dependency wait longer than this aborts the run with [PanguLU ERROR]
 };
@@ -1311,6 +1312,8 @@ void launch_mega(pangulu_sm100_plan* pl)
         const int gmax = (int)std::min<long long>(16, std::max<long long>(1, g.opt.ct_gmax)), minst = (int)std::min<long long>(8, std::max<long long>(2, g.opt.ct_minst));
         CK(cudaMemcpyToSymbolAsync(g_ct_gmax, &gmax, sizeof gmax, 0, cudaMemcpyHostToDevice, g.stream));
         CK(cudaMemcpyToSymbolAsync(g_ct_minst, &minst, sizeof minst, 0, cudaMemcpyHostToDevice, g.stream));
+        const int defer = (int)std::min<long long>(PSM_DEFER_MAX, std::max<long long>(0, g.opt.defer));
+        CK(cudaMemcpyToSymbolAsync(g_defer_depth, &defer, sizeof defer, 0, cudaMemcpyHostToDevice, g.stream));
     }
     if (pl->nb <= 128)
     {
@@ -1578,6 +1581,7 @@ static long long* option_slot(const char* key)
     if (!strcmp(key, "dense_all_panels")) return &g.opt.dense_all_panels;
     if (!strcmp(key, "spin_timeout_ms")) return &g.opt.spin_timeout_ms;
     if (!strcmp(key, "progress")) return &g.opt.progress;
+    if (!strcmp(key, "defer")) return &g.opt.defer;
     if (!strcmp(key, "ct_gmax")) return &g.opt.ct_gmax;
     if (!strcmp(key, "ct_minst")) return &g.opt.ct_minst;
     return nullptr;

@@ -1446,6 +1446,56 @@ __device__ __forceinline__ void stage_copy(void* dst, const void* src, size_t by
     for (size_t k = nvec * 16 + tid; k < bytes; k += nthreads) db[k] = sb[k];
 }
 
+// Have the dependencies of task t arrived?  One warp, non-blocking (the same flags and counters the task's own blocking
+// waits look at; those waits still run afterwards and carry the ordering).
+template <class T>
+__device__ __forceinline__ bool task_ready(const MegaParams<T>& P, int t, int lane)
+{
+    const MegaTask mt = P.tasks[t];
+    bool ok = true;
+    auto flag = [&](int id) { return id < 0 || (P.multi ? ld_acquire_sys(P.done + id) : ld_acquire(P.done + id)) != 0; };
+    switch (mt.kind)
+    {
+    case MEGA_TILE:
+    case MEGA_SPARSE:
+    case MEGA_CTILE:
+    {
+        const SsssmDest<T>* D = P.dests + mt.a;
+        const u32 pb = D->pair_begin, pe = D->pair_end;
+        const int2* deps = mt.kind == MEGA_CTILE ? P.cpair_dep : P.pair_dep;
+        for (u32 p = pb + lane; p < pe && ok; p += PSM_WARP)
+        {
+            const int2 dep = deps[p];
+            ok = flag(dep.x) && flag(dep.y);
+        }
+        break;
+    }
+    case MEGA_GETRF_SMEM:
+    case MEGA_GETRF_DENSE:
+    case MEGA_GETRF_GLOBAL:
+        ok = ld_acquire(P.remaining + P.getrf_id[mt.a].x) == 0;
+        break;
+    case MEGA_DDENS:
+    {
+        const int2 id = P.getrf_id[mt.a];
+        ok = flag(id.x) && flag(id.y);
+        break;
+    }
+    case MEGA_CPANEL:
+    case MEGA_PANEL:
+    {
+        const int panel = mt.kind == MEGA_CPANEL ? P.cptasks[mt.a].panel : mt.a;
+        const int4 dp = P.panel_dep[panel];
+        ok = flag(dp.x) && flag(dp.y) && flag(dp.z) && flag(dp.w) && ld_acquire(P.remaining + P.panel_id[panel].x) == 0;
+        break;
+    }
+    }
+    return __all_sync(PSM_FULL, ok);
+}
+
+#define PSM_DEFER_MAX 8
+__device__ int g_defer_depth = 0;   // option "defer": tasks a CTA may set aside while their dependencies are outstanding
+
 template <class T, int TM>
 __global__ void __launch_bounds__(512, 1)
 mega_kernel(const MegaParams<T> P)
@@ -1453,18 +1503,85 @@ mega_kernel(const MegaParams<T> P)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ int s_ticket;
     __shared__ int s_last;
+    __shared__ int s_def[PSM_DEFER_MAX], s_ndef, s_exhausted;
     const int tid = threadIdx.x, warp = tid / PSM_WARP;
     const int nb = P.nb;
     CtState ct_state;
     CpState cp_state;
+    const int defer_depth = min(PSM_DEFER_MAX, max(0, g_defer_depth));
+    if (tid == 0) { s_ndef = 0; s_exhausted = 0; }
+    __syncthreads();
     for (;;)
     {
-        if (tid == 0) s_ticket = atomicAdd(P.counter, 1);
+        if (defer_depth == 0)
+        {
+            if (tid == 0) s_ticket = atomicAdd(P.counter, 1);
+        }
+        else if (warp == 0)
+        {
+            // Choose the next task.  A task whose dependencies are outstanding is SET ASIDE (at most defer_depth of them) and the
+            // CTA goes on with the list, instead of holding its SM while it waits -- with several ranks a third of the SM time
+            // went into such waits at the head of the list.  Progress: the CTA polls what it set aside before every new
+            // ticket; with a full set-aside list it takes the OLDEST entry and waits for it in place (the globally oldest
+            // unfinished task is always ready and is either running or the oldest entry of the CTA that holds it).
+            const int lane = tid;
+            int pick = -1;
+            for (int i = 0; i < s_ndef && pick < 0; ++i)
+            {
+                const int cand = s_def[i];
+                if (task_ready<T>(P, cand, lane))
+                {
+                    pick = cand;
+                    __syncwarp();
+                    if (lane == 0) { for (int j = i; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_ndef = s_ndef - 1; }
+                    __syncwarp();
+                }
+            }
+            while (pick < 0)
+            {
+                if (!s_exhausted)
+                {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(P.counter, 1);
+                    t = __shfl_sync(PSM_FULL, t, 0);
+                    if (t >= P.ntask)
+                    {
+                        if (lane == 0) s_exhausted = 1;
+                        __syncwarp();
+                        continue;
+                    }
+                    if (P.trace && lane == 0) P.trace[3 * (size_t)t] = global_ns();
+                    if (task_ready<T>(P, t, lane)) pick = t;
+                    else if (s_ndef < defer_depth)
+                    {
+                        if (lane == 0) { s_def[s_ndef] = t; s_ndef = s_ndef + 1; }
+                        __syncwarp();
+                    }
+                    else
+                    {
+                        // full: run the oldest entry (its waits block in place), the new task takes its slot at the back
+                        pick = s_def[0];
+                        __syncwarp();
+                        if (lane == 0) { for (int j = 0; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_def[s_ndef - 1] = t; }
+                        __syncwarp();
+                    }
+                }
+                else if (s_ndef == 0) pick = P.ntask;   // nothing left anywhere
+                else
+                {
+                    pick = s_def[0];
+                    __syncwarp();
+                    if (lane == 0) { for (int j = 0; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_ndef = s_ndef - 1; }
+                    __syncwarp();
+                }
+            }
+            if (lane == 0) s_ticket = pick;
+        }
         __syncthreads();
         const int t = s_ticket;
         if (t >= P.ntask) break;
         const MegaTask mt = P.tasks[t];
-        if (P.trace && tid == 0) P.trace[3 * (size_t)t] = global_ns();
+        if (P.trace && tid == 0 && defer_depth == 0) P.trace[3 * (size_t)t] = global_ns();
         if (P.progress && tid == 0)
         {
             volatile int* pg = reinterpret_cast<volatile int*>(P.progress + blockIdx.x);
