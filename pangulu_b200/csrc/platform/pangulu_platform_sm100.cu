@@ -48,8 +48,9 @@ void dump_progress()
     {
         const int4 v = g_progress_host[b];
         if (v.w == 2) continue;   // finished its last task
-        fprintf(stderr, "[PanguLU ERROR]   CTA %3d: task %d kind %s arg %d state %s\n", b, v.x, (v.y >= 0 && v.y < 9) ? kinds[v.y] : "?", v.z,
-                v.w == 0 ? "waiting for dependencies" : "running");
+        const int4 q = g_progress_host[512 + b];
+        fprintf(stderr, "[PanguLU ERROR]   CTA %3d: task %d kind %s arg %d state %s  set aside: %d %d %d %d\n", b, v.x, (v.y >= 0 && v.y < 9) ? kinds[v.y] : "?", v.z,
+                v.w == 0 ? "waiting for dependencies" : "running", q.x, q.y, q.z, q.w);
 
     }
 }
@@ -1301,7 +1302,7 @@ void launch_mega(pangulu_sm100_plan* pl)
             CK(cudaHostAlloc((void**)&g_progress_host, sizeof(int4) * 1024, cudaHostAllocMapped));
             g_progress_ctas = grid;
         }
-        for (int b = 0; b < 1024; ++b) g_progress_host[b] = make_int4(-1, -1, 0, 2);
+        for (int b = 0; b < 1024; ++b) g_progress_host[b] = b < 512 ? make_int4(-1, -1, 0, 2) : make_int4(-1, -1, -1, -1);
         CK(cudaHostGetDevicePointer((void**)&mp.progress, g_progress_host, 0));
     }
     {

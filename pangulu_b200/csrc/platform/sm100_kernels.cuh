@@ -1524,58 +1524,59 @@ mega_kernel(const MegaParams<T> P)
             // went into such waits at the head of the list.  Progress: the CTA polls what it set aside before every new
             // ticket; with a full set-aside list it takes the OLDEST entry and waits for it in place (the globally oldest
             // unfinished task is always ready and is either running or the oldest entry of the CTA that holds it).
+            // The list lives in shared memory, its LENGTH and the exhausted flag in registers of every lane (all lanes take
+            // the same branches; branching on shared state that lane 0 is changing would let the lanes disagree).
             const int lane = tid;
+            int ndef = s_ndef, exhausted = s_exhausted;
+            __syncwarp();
+            auto drop = [&](int i) {   // remove entry i (all lanes call it)
+                __syncwarp();
+                if (lane == 0) for (int j = i; j + 1 < ndef; ++j) s_def[j] = s_def[j + 1];
+                --ndef;
+                __syncwarp();
+            };
             int pick = -1;
-            for (int i = 0; i < s_ndef && pick < 0; ++i)
+            for (int i = 0; i < ndef && pick < 0; ++i)
             {
                 const int cand = s_def[i];
-                if (task_ready<T>(P, cand, lane))
-                {
-                    pick = cand;
-                    __syncwarp();
-                    if (lane == 0) { for (int j = i; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_ndef = s_ndef - 1; }
-                    __syncwarp();
-                }
+                if (task_ready<T>(P, cand, lane)) { pick = cand; drop(i); }
             }
             while (pick < 0)
             {
-                if (!s_exhausted)
+                if (!exhausted)
                 {
                     int t = 0;
                     if (lane == 0) t = atomicAdd(P.counter, 1);
                     t = __shfl_sync(PSM_FULL, t, 0);
-                    if (t >= P.ntask)
-                    {
-                        if (lane == 0) s_exhausted = 1;
-                        __syncwarp();
-                        continue;
-                    }
+                    if (t >= P.ntask) { exhausted = 1; continue; }
                     if (P.trace && lane == 0) P.trace[3 * (size_t)t] = global_ns();
                     if (task_ready<T>(P, t, lane)) pick = t;
-                    else if (s_ndef < defer_depth)
+                    else if (ndef < defer_depth)
                     {
-                        if (lane == 0) { s_def[s_ndef] = t; s_ndef = s_ndef + 1; }
+                        __syncwarp();
+                        if (lane == 0) s_def[ndef] = t;
+                        ++ndef;
                         __syncwarp();
                     }
                     else
                     {
-                        // full: run the oldest entry (its waits block in place), the new task takes its slot at the back
+                        // full: run the oldest entry (its waits block in place), the new task goes to the back of the list
                         pick = s_def[0];
-                        __syncwarp();
-                        if (lane == 0) { for (int j = 0; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_def[s_ndef - 1] = t; }
+                        drop(0);
+                        if (lane == 0) s_def[ndef] = t;
+                        ++ndef;
                         __syncwarp();
                     }
                 }
-                else if (s_ndef == 0) pick = P.ntask;   // nothing left anywhere
-                else
-                {
-                    pick = s_def[0];
-                    __syncwarp();
-                    if (lane == 0) { for (int j = 0; j + 1 < s_ndef; ++j) s_def[j] = s_def[j + 1]; s_ndef = s_ndef - 1; }
-                    __syncwarp();
-                }
+                else if (ndef == 0) pick = P.ntask;   // nothing left anywhere
+                else { pick = s_def[0]; drop(0); }
             }
-            if (lane == 0) s_ticket = pick;
+            if (lane == 0) { s_ticket = pick; s_ndef = ndef; s_exhausted = exhausted; }
+            if (P.progress && lane == 0)
+            {
+                volatile int* pd = reinterpret_cast<volatile int*>(P.progress + 512 + blockIdx.x);
+                for (int j = 0; j < 4; ++j) pd[j] = j < ndef ? s_def[j] : -1;
+            }
         }
         __syncthreads();
         const int t = s_ticket;
