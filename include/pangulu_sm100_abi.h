@@ -28,6 +28,15 @@
 #endif
 #define PANGULU_PLATFORM_ENV
 #include "pangulu_common.h"
+#if defined(__cplusplus)
+/* helper pair types of the kernels (real value types only in this mode: PanguLU's header gives a C++ translation unit
+ * `double _Complex`, which the kernels do not take) */
+struct pangulu_sm100_c64 { double re, im; };
+struct pangulu_sm100_c32 { float re, im; };
+#if defined(CALCULATE_TYPE_CR64) || defined(CALCULATE_TYPE_CR32)
+#error "PANGULU_SM100_USE_REFERENCE_HEADER supports the real value types; build the complex types with the restated header"
+#endif
+#endif
 #else
 
 #if !defined(CALCULATE_TYPE_R64) && !defined(CALCULATE_TYPE_R32) && !defined(CALCULATE_TYPE_CR64) && !defined(CALCULATE_TYPE_CR32)
