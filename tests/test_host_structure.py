@@ -126,19 +126,23 @@ def test_block_cyclic_ownership_partitions_the_tasks(nproc, split):
     A = matrices.poisson3d(10)
     nb = 32
     key = lambda t: (int(t["row"]), int(t["col"]), int(t["kernel_id"]), int(t["task_level"]), int(t["compare_flag"]) >> 32)
+    waves = lambda wp: np.repeat(np.arange(len(wp) - 1), np.diff(wp.astype(np.int64)))
     base = PanguLU(A, nb=nb, host_only=True, split_diag=split)
-    t0, _ = base.schedule()
-    all_tasks = sorted(key(t) for t in t0)
+    t0, wp0 = base.schedule()
+    all_tasks = sorted(key(t) + (int(w),) for t, w in zip(t0, waves(wp0)))
     base.finalize()
     got = []
     pq = {2: (1, 2), 4: (2, 2), 8: (2, 4)}[nproc]
     for r in range(nproc):
         s = PanguLU(A, nb=nb, host_only=True, rank=r, nproc=nproc, split_diag=split)
         assert (int(s.info("p")), int(s.info("q"))) == pq
-        t, _ = s.schedule()
+        t, wp = s.schedule()
         for x in t:
             assert (int(x["row"]) % pq[0]) * pq[1] + int(x["col"]) % pq[1] == r
-        got += [key(x) for x in t]
+        # the wave of a task is part of the key: every rank places a task in the wave the single-rank schedule gives it, so the
+        # waves are ONE global order in which every dependency -- local or on another rank -- points backwards.  That is what
+        # keeps the persistent executors of several ranks, each fetching its own list in order, free of circular waits.
+        got += [key(x) + (int(w),) for x, w in zip(t, waves(wp))]
         s.finalize()
     assert sorted(got) == all_tasks
 

@@ -48,7 +48,7 @@ def _live_ref():
         pytest.skip("oracle/_ref not built on this box")
 
 
-@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64"])
+@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64", "cr32"])
 def test_oracle_kernels_match_reference_platform_kernels(vtype):
     """Per kernel, on blocks of a 3D Poisson matrix with random values: oracle vs pangulu_platform_0100000_*
     called directly (GETRF/TSTRF/GESSM bit for bit, SSSSM to rounding)."""
@@ -59,7 +59,7 @@ def test_oracle_kernels_match_reference_platform_kernels(vtype):
     from helpers import blocks_of
 
     nb = 16
-    dtype = np.dtype({"r64": np.float64, "r32": np.float32, "cr64": np.complex128}[vtype])
+    dtype = np.dtype({"r64": np.float64, "r32": np.float32, "cr64": np.complex128, "cr32": np.complex64}[vtype])
     blocks = blocks_of(matrices.poisson3d(6), nb, vtype)
     rng = np.random.default_rng(3)
     for b in blocks:
@@ -71,7 +71,7 @@ def test_oracle_kernels_match_reference_platform_kernels(vtype):
     lo = next(b for b in blocks if b.brow == b.bcol == 0 and not b.is_upper)
     up = next(b for b in blocks if b.brow == b.bcol == 0 and b.is_upper)
     R, O = RefLib(vtype), Oracle(vtype)
-    tol = 1e-5 if vtype == "r32" else 1e-13
+    tol = 1e-5 if vtype in ("r32", "cr32") else 1e-13
 
     def ref_slot(b):
         return R.make_slot(b.brow, b.bcol, b.is_upper, b.colptr, b.rowidx, b.value, b.rowptr, b.colidx, b.csr2csc)
@@ -109,7 +109,7 @@ def test_oracle_kernels_match_reference_platform_kernels(vtype):
     assert n_t and n_g and n_s
 
 
-@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64"])
+@pytest.mark.parametrize("vtype", ["r64", "r32", "cr64", "cr32"])
 def test_oracle_solve_kernels_match_reference_platform_kernels(vtype):
     """spmv / sptrsv of the solve phase (pangulu_platform_0100000.c:433-506): the oracle's restatement against the reference
     CPU platform called directly, bit for bit (same operations in the same order)."""
@@ -120,7 +120,7 @@ def test_oracle_solve_kernels_match_reference_platform_kernels(vtype):
     from helpers import blocks_of
 
     nb = 16
-    dtype = np.dtype({"r64": np.float64, "r32": np.float32, "cr64": np.complex128}[vtype])
+    dtype = np.dtype({"r64": np.float64, "r32": np.float32, "cr64": np.complex128, "cr32": np.complex64}[vtype])
     blocks = blocks_of(matrices.poisson3d(6), nb, vtype)
     rng = np.random.default_rng(5)
     rnd = lambda shape: (rng.uniform(-1, 1, shape) + (1j * rng.uniform(-1, 1, shape) if dtype.kind == "c" else 0)).astype(dtype)
