@@ -273,6 +273,26 @@ def measured_traffic(label):
         return json.load(f).get(label)
 
 
+def recorded_full_size_reference(label):
+    """NOT measured by this run: the one-off run of the unmodified reference CPU platform on the FULL configuration `label`
+    (scripts/ref_cpu_full_size.py; profiles/r02_reference_cpu_full_*.json name host, ranks and date), quoted so that the
+    same-configuration CPU figure stands next to the bounded sample the reference arm can afford per step."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_reference_cpu_full_100cubed.json")) as f:
+            d = json.load(f)
+        runs = [{"workload": "poisson3d_7pt_100^3_r64_metis_nb256", "t_gstrf_s": d["t_gstrf_s"], "gflops": d["gflops"], "ranks": d["ranks"], "host": d["host"]}]
+        with open(os.path.join(ROOT, "profiles", "r02_reference_cpu_full_other_configs.json")) as f:
+            o = json.load(f)
+        runs += [{"workload": r["workload"], "t_gstrf_s": r["t_gstrf_s"], "gflops": r["gflops"], "ranks": r["ranks"], "host": d["host"]} for r in o["runs"]]
+        for r in runs:
+            if r["workload"] == label:
+                r["note"] = "recorded one-off run (profiles/r02_reference_cpu_full_*.json), not timed by this bench run"
+                return r
+    except Exception:
+        pass
+    return None
+
+
 def time_resident(s, L, steps, warmup, world, dist, stream, torch, sampler=None):
     """W untimed + K timed factorisations on values resident in HBM; CUDA events on the module's stream, max over ranks."""
     times = []
@@ -571,7 +591,7 @@ def run_ours(a):
                        "l2": "inputs (factor values %.1f GB) exceed the 126 MB L2; values are rewritten between steps" % (s.info("value_bytes") / 1e9),
                        "init_seconds": init},
             "clocks": clocks, "e2e": e2e, "e2e_resident": e2e_resident, "gpu_launches": launches, "roofline": roof, "classes": classes, "cpu_baseline": cpu,
-            "same_config_sample": sample,
+            "same_config_sample": sample, "reference_cpu_full_size_recorded": recorded_full_size_reference(label),
             "parity": {"factor_check_resident": check, "factor_check_e2e": check_e2e,
                        "what": "||L(U 1) - A 1|| / ||A 1|| of the factors just timed; several ranks: partial products summed over the ranks"}}
     s.finalize()
